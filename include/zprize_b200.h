@@ -1,0 +1,179 @@
+/* C-ABI of the B200-native PLONK prover hot path (libzprize_b200.so).
+ *
+ * Drop-in boundary: `gen_proof` below has exactly the signature the reference binds from Rust
+ *   extern "C" { pub fn gen_proof(circuit: CircuitC, pk: ProverKeyC, ck: CommitKeyC) -> ProofC; }
+ *   ("Prize 1B/plonk-core/src/lib.rs":237-239; C++ side "Prize 1B/plonk-core/lib/hello.cu":4-7), and the
+ * structs are field-for-field the `#[repr(C)]` structs of lib.rs:53-235 (mirrored in C by the reference at
+ * "Prize 1B/plonk-core/lib/PLONK/src/structure.cuh":7-329).  Everything else in this header is an
+ * extension (resident prover context, per-operator entry points for the NTT / MSM sweeps) — plain
+ * pointers and sizes only.
+ *
+ * Data conventions (all identical to the reference FFI):
+ *   Fr  = 4 x u64 little-endian limbs, Montgomery form (R = 2^256), canonical (< r)
+ *   Fq  = 6 x u64 little-endian limbs, Montgomery form (R = 2^384)
+ *   G1 affine = x || y (12 x u64), no infinity flag; infinity in outputs is (x = 0, y = Mont(1))
+ *   CircuitC.pi is ONE Fr in canonical (non-Montgomery) form (prover.rs:721-725)
+ */
+#ifndef ZPRIZE_B200_H
+#define ZPRIZE_B200_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- lib.rs:53-118 ------------------------------------------------------------------------ */
+typedef struct { uint64_t a_eval[4], b_eval[4], c_eval[4], d_eval[4]; } WireEvaluationsC;
+typedef struct { uint64_t left_sigma_eval[4], right_sigma_eval[4], out_sigma_eval[4], permutation_eval[4]; } PermutationEvaluationsC;
+typedef struct {
+    uint64_t q_lookup_eval[4], z2_next_eval[4], h1_eval[4], h1_next_eval[4], h2_eval[4], f_eval[4], table_eval[4],
+        table_next_eval[4];
+} LookupEvaluationsC;
+typedef struct {
+    uint64_t q_arith_eval[4], q_c_eval[4], q_l_eval[4], q_r_eval[4], q_hl_eval[4], q_hr_eval[4], q_h4_eval[4], a_next_eval[4],
+        b_next_eval[4], d_next_eval[4];
+} CustomEvaluationsC;
+typedef struct {
+    WireEvaluationsC wire_evals;
+    PermutationEvaluationsC perm_evals;
+    LookupEvaluationsC lookup_evals;
+    CustomEvaluationsC custom_evals;
+} ProofEvaluationsC;
+
+/* lib.rs:231-235 */
+typedef struct { uint64_t x[6]; uint64_t y[6]; } CommitmentC;
+
+/* lib.rs:120-142 */
+typedef struct {
+    CommitmentC a_comm, b_comm, c_comm, d_comm, z_comm, f_comm, h_1_comm, h_2_comm, z_2_comm;
+    CommitmentC t_1_comm, t_2_comm, t_3_comm, t_4_comm, t_5_comm, t_6_comm, t_7_comm, t_8_comm;
+    CommitmentC aw_opening, saw_opening;
+    ProofEvaluationsC evaluations;
+} ProofC;
+
+/* lib.rs:144-155 */
+typedef struct {
+    uint64_t n;               /* unpadded gate count cs.n */
+    uint64_t lookup_len;      /* rows of the lookup table */
+    uint64_t intended_pi_pos; /* position of the single public input */
+    uint64_t* q_lookup;       /* n Fr */
+    uint64_t* pi;             /* 1 Fr, canonical form */
+    uint64_t* w_l;            /* n Fr each */
+    uint64_t* w_r;
+    uint64_t* w_o;
+    uint64_t* w_4;
+} CircuitC;
+
+/* lib.rs:157-223 — *_coeffs: <= N Fr (arkworks trims trailing zeros; see zp_prover_load_pk for how
+ * identically-zero polynomials are handled), *_evals: 8N Fr on the coset g*H_8N, natural order. */
+typedef struct {
+    uint64_t *q_m_coeffs, *q_m_evals;
+    uint64_t *q_l_coeffs, *q_l_evals;
+    uint64_t *q_r_coeffs, *q_r_evals;
+    uint64_t *q_o_coeffs, *q_o_evals;
+    uint64_t *q_4_coeffs, *q_4_evals;
+    uint64_t *q_c_coeffs, *q_c_evals;
+    uint64_t *q_hl_coeffs, *q_hl_evals;
+    uint64_t *q_hr_coeffs, *q_hr_evals;
+    uint64_t *q_h4_coeffs, *q_h4_evals;
+    uint64_t *q_arith_coeffs, *q_arith_evals;
+    uint64_t *range_selector_coeffs, *range_selector_evals;
+    uint64_t *logic_selector_coeffs, *logic_selector_evals;
+    uint64_t *fixed_group_add_selector_coeffs, *fixed_group_add_selector_evals;
+    uint64_t *variable_group_add_selector_coeffs, *variable_group_add_selector_evals;
+    uint64_t *q_lookup_coeffs, *q_lookup_evals;
+    uint64_t *table1, *table2, *table3, *table4; /* N Fr each */
+    uint64_t *left_sigma_coeffs, *left_sigma_evals;
+    uint64_t *right_sigma_coeffs, *right_sigma_evals;
+    uint64_t *out_sigma_coeffs, *out_sigma_evals;
+    uint64_t *fourth_sigma_coeffs, *fourth_sigma_evals;
+    uint64_t* linear_evaluations; /* 8N — closed form, never read */
+    uint64_t* v_h_coset_8n;       /* 8N — closed form, never read */
+} ProverKeyC;
+
+/* lib.rs:225-229 */
+typedef struct {
+    const uint64_t* powers_of_g;       /* >= N affine points */
+    const uint64_t* powers_of_gamma_g; /* unused (hiding is off) */
+} CommitKeyC;
+
+/* ---- the drop-in symbol (lib.rs:237-239) ------------------------------------------------------
+ * Uploads the prover key and SRS on the first call for a given (pk, ck) pointer set and keeps them
+ * resident in HBM for later calls (disable with ZPRIZE_B200_PK_CACHE=0).
+ * Like the reference it has no error channel: a CUDA failure prints a message and exits(1). */
+ProofC gen_proof(CircuitC circuit, ProverKeyC pk, CommitKeyC ck);
+
+/* ---- resident prover context (extension) ------------------------------------------------------ */
+typedef struct zp_prover zp_prover;
+
+/* last error message of the calling thread ("" if none) */
+const char* zp_last_error(void);
+/* number of CUDA kernels launched by the library so far (process-wide) */
+uint64_t zp_launch_count(void);
+/* 1 if a CUDA device is usable */
+int zp_device_available(void);
+
+/* Context for domain size N = 2^log_n on the current CUDA device. NULL on error. */
+zp_prover* zp_prover_create(int log_n);
+void zp_prover_destroy(zp_prover* p);
+/* transcript label; default "Merkle tree" (gen_proof.cuh:19-20) */
+int zp_prover_set_label(zp_prover* p, const char* label);
+/* SRS: n_points affine points (CommitKeyC.powers_of_g layout), n_points >= N. */
+int zp_prover_load_srs(zp_prover* p, const uint64_t* powers_of_g, size_t n_points);
+/* Insecure test SRS generated on the device: powers_of_g[i] = tau^i * G (tau: Montgomery Fr). */
+int zp_prover_generate_srs(zp_prover* p, const uint64_t* tau, size_t n_points);
+/* Copy the resident SRS back (n_points * 12 u64). */
+int zp_prover_read_srs(zp_prover* p, uint64_t* out, size_t n_points);
+/* Upload a prover key given in the reference FFI layout.  coeff_len[19] gives the readable length of
+ * each *_coeffs array in ProverKeyC order (q_m .. q_lookup, then the four sigmas); pass NULL to apply
+ * the reference's convention (gen_proof.cuh:61-62,277-278,319-329): q_m, range, logic, fixed, variable
+ * and q_lookup coefficient arrays are NOT read (they are recovered from the *_evals arrays), all
+ * others hold exactly N elements. */
+int zp_prover_load_pk(zp_prover* p, const ProverKeyC* pk, const uint64_t* coeff_len);
+/* Build the prover key ON THE DEVICE from the circuit description (preprocessing,
+ * "Prize 1B/plonk-core/src/proof_system/preprocess.rs":162-295): selector_evals[19] are the 15 selector
+ * columns followed by the 4 sigma columns as evaluations on H (N Fr each, host memory, NULL = all
+ * zero); tables[4] the padded lookup columns (N Fr each, NULL = all zero). */
+int zp_prover_preprocess(zp_prover* p, const uint64_t* const* selector_evals, const uint64_t* const* tables);
+/* Commitments to the 19 prover-key polynomials + 4 table polynomials (verifier key), 23 * 12 u64. */
+int zp_prover_verifier_key(zp_prover* p, uint64_t* out_commitments);
+/* One proof with the resident key.  Host pointers in `circuit`; returns 0 on success. */
+int zp_prover_prove(zp_prover* p, const CircuitC* circuit, ProofC* out);
+/* Device-milliseconds of the phases of the last proof: [0] total, [1] NTT, [2] MSM, [3] quotient,
+ * [4] other (CUDA events on the prover's stream). */
+int zp_prover_last_timing(zp_prover* p, double* out_ms, int n);
+
+/* ---- operator entry points for the sweeps (function.cuh:45-113 equivalents) ------------------ */
+/* kind: 0 NTT, 1 iNTT, 2 coset-NTT (g = 7), 3 coset-iNTT; natural order in/out; host buffers. */
+int zp_ntt_host(zp_prover* p, int kind, int log_n, const uint64_t* in, uint64_t* out);
+/* MSM over the first n points of the resident SRS with n host scalars (Montgomery Fr). out: affine. */
+int zp_msm_host(zp_prover* p, const uint64_t* scalars, size_t n, uint64_t* out_affine);
+/* MSM with caller-supplied points (n * 12 u64, host). window_bits = 0 picks the default. */
+int zp_msm_points_host(zp_prover* p, const uint64_t* points, const uint64_t* scalars, size_t n, int window_bits,
+                       uint64_t* out_affine);
+/* p(z) for a host coefficient array */
+int zp_poly_eval_host(zp_prover* p, const uint64_t* coeffs, size_t n, const uint64_t* point, uint64_t* out);
+/* floor(p / (X - z)) for a host coefficient array (n - 1 coefficients out) */
+int zp_poly_divide_host(zp_prover* p, const uint64_t* coeffs, size_t n, const uint64_t* point, uint64_t* out);
+/* exclusive prefix product (the z(X) scan primitive) */
+int zp_prefix_product_host(zp_prover* p, const uint64_t* in, size_t n, uint64_t* out);
+
+/* device-resident variants used by bench.py for kernel-only timing: buffers owned by the context */
+int zp_bench_alloc(zp_prover* p, int slot, size_t n_fr);               /* slot 0..7 */
+int zp_bench_upload(zp_prover* p, int slot, const uint64_t* host, size_t n_fr);
+int zp_bench_download(zp_prover* p, int slot, uint64_t* host, size_t n_fr);
+/* runs `iters` transforms slot_in -> slot_out on the stream; returns average device ms via *ms */
+int zp_bench_ntt(zp_prover* p, int kind, int log_n, int slot_in, int slot_out, int iters, double* ms);
+/* runs `iters` MSMs of n points with scalars in `slot`; *ms = average device ms (host tail included) */
+int zp_bench_msm(zp_prover* p, int slot, size_t n, int iters, double* ms, uint64_t* out_affine);
+/* per-kernel device time of the last zp_bench_msm iteration: digits, scan, scatter, accumulate, reduce */
+int zp_bench_msm_breakdown(zp_prover* p, double* ms5);
+/* integer-pipe microbenchmark: mode 0 = IMAD (mad.lo), 1 = IMAD.WIDE (mad.wide), 2 = Fq Montgomery
+ * products; returns giga-operations per second (ops = instructions for 0/1, field products for 2) */
+int zp_bench_int_pipe(zp_prover* p, int mode, double* gops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZPRIZE_B200_H */

@@ -1,0 +1,379 @@
+// extern "C" surface of libzprize_b200.so — see include/zprize_b200.h for the contract of every symbol.
+#include "prover.cuh"
+#include <chrono>
+#include <map>
+#include <mutex>
+
+using namespace zp;
+
+namespace {
+thread_local std::string g_err;
+template <class F>
+int guard(F&& f) {
+    try {
+        f();
+        g_err.clear();
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+struct BenchState {
+    DevBuf<fr_t> slot[8];
+    double msm_ms[5] = {0, 0, 0, 0, 0};
+};
+std::map<zp_prover*, BenchState*> g_bench;
+BenchState& bench_of(zp_prover* p) {
+    auto it = g_bench.find(p);
+    if (it == g_bench.end()) it = g_bench.emplace(p, new BenchState()).first;
+    return *it->second;
+}
+inline Prover* P(zp_prover* p) { return reinterpret_cast<Prover*>(p); }
+}  // namespace
+
+extern "C" {
+
+const char* zp_last_error(void) { return g_err.c_str(); }
+uint64_t zp_launch_count(void) { return g_launch_count; }
+int zp_device_available(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n > 0;
+}
+
+zp_prover* zp_prover_create(int log_n) {
+    Prover* p = nullptr;
+    if (guard([&] {
+            if (!zp_device_available()) throw std::runtime_error("no CUDA device: libzprize_b200 has no CPU fallback");
+            p = new Prover(log_n);
+        }))
+        return nullptr;
+    return reinterpret_cast<zp_prover*>(p);
+}
+void zp_prover_destroy(zp_prover* p) {
+    auto it = g_bench.find(p);
+    if (it != g_bench.end()) {
+        delete it->second;
+        g_bench.erase(it);
+    }
+    delete P(p);
+}
+int zp_prover_set_label(zp_prover* p, const char* label) { return guard([&] { P(p)->label = label; }); }
+int zp_prover_load_srs(zp_prover* p, const uint64_t* pts, size_t n) { return guard([&] { P(p)->load_srs(pts, n); }); }
+int zp_prover_generate_srs(zp_prover* p, const uint64_t* tau, size_t n) {
+    return guard([&] {
+        fr_t t;
+        memcpy(t.l, tau, 32);
+        P(p)->generate_srs(t, n);
+    });
+}
+int zp_prover_read_srs(zp_prover* p, uint64_t* out, size_t n) {
+    return guard([&] {
+        Prover* pr = P(p);
+        if (n > pr->srs.n) throw std::runtime_error("zp_prover_read_srs: more points than resident");
+        ZP_CUDA(cudaMemcpy(out, pr->srs.p, n * sizeof(affine_t), cudaMemcpyDeviceToHost));
+    });
+}
+int zp_prover_load_pk(zp_prover* p, const ProverKeyC* pk, const uint64_t* coeff_len) {
+    return guard([&] { P(p)->load_pk(*pk, coeff_len); });
+}
+int zp_prover_preprocess(zp_prover* p, const uint64_t* const* selector_evals, const uint64_t* const* tables) {
+    return guard([&] { P(p)->preprocess(selector_evals, tables); });
+}
+int zp_prover_verifier_key(zp_prover* p, uint64_t* out) { return guard([&] { P(p)->verifier_key(out); }); }
+int zp_prover_prove(zp_prover* p, const CircuitC* c, ProofC* out) { return guard([&] { P(p)->prove(*c, out); }); }
+int zp_prover_last_timing(zp_prover* p, double* out_ms, int n) {
+    return guard([&] {
+        for (int i = 0; i < n && i < 5; i++) out_ms[i] = P(p)->last_ms[i];
+    });
+}
+
+// ---- the reference's own symbol -------------------------------------------------------------------
+// Keeps one resident context per (domain size, pk pointer set, ck pointer); a sampled content
+// fingerprint guards against the caller recycling the same addresses for a different key.
+namespace {
+struct CacheEntry {
+    Prover* prover = nullptr;
+    ProverKeyC pk;
+    const uint64_t* ck = nullptr;
+    int logn = 0;
+    uint64_t fingerprint = 0;
+};
+CacheEntry g_cache;
+std::mutex g_cache_mu;
+uint64_t fingerprint_of(const ProverKeyC& pk, const CommitKeyC& ck, size_t n) {
+    uint64_t h = 0xcbf29ce484222325ULL;
+    auto mix = [&](const uint64_t* p, size_t words) {
+        for (size_t i = 0; i < words; i++) h = (h ^ p[i]) * 0x100000001b3ULL;
+    };
+    const uint64_t* arrays[] = {pk.q_l_evals, pk.q_r_evals, pk.q_o_evals, pk.q_c_evals, pk.q_arith_evals, pk.left_sigma_evals,
+                                pk.fourth_sigma_evals, pk.q_hl_evals};
+    for (const uint64_t* a : arrays) {
+        mix(a, 64);
+        mix(a + 4 * (4 * n + 17), 64);
+        mix(a + 4 * (8 * n - 16), 64);
+    }
+    mix(ck.powers_of_g, 48);
+    mix(ck.powers_of_g + 12 * (n - 4), 48);
+    return h;
+}
+}  // namespace
+
+ProofC gen_proof(CircuitC circuit, ProverKeyC pk, CommitKeyC ck) {
+    ProofC proof;
+    memset(&proof, 0, sizeof(proof));
+    try {
+        if (!zp_device_available()) throw std::runtime_error("no CUDA device: libzprize_b200 has no CPU fallback");
+        std::lock_guard<std::mutex> lock(g_cache_mu);
+        // domain size as the reference derives it (lib/PLONK/src/composer.cu:3-21)
+        size_t bound = circuit.n > circuit.lookup_len ? circuit.n : circuit.lookup_len;
+        int logn = ilog2(bound);
+        if (logn < 6) logn = 6;
+        size_t n = (size_t)1 << logn;
+        const char* env = getenv("ZPRIZE_B200_PK_CACHE");
+        bool use_cache = !(env && env[0] == '0');
+        uint64_t fp = fingerprint_of(pk, ck, n);
+        bool hit = use_cache && g_cache.prover && g_cache.logn == logn && g_cache.ck == ck.powers_of_g &&
+                   memcmp(&g_cache.pk, &pk, sizeof(pk)) == 0 && g_cache.fingerprint == fp;
+        if (!hit) {
+            delete g_cache.prover;
+            g_cache.prover = nullptr;
+            Prover* p = new Prover(logn);
+            g_cache.prover = p;
+            p->load_srs(ck.powers_of_g, n);
+            p->load_pk(pk, nullptr);
+            g_cache.pk = pk;
+            g_cache.ck = ck.powers_of_g;
+            g_cache.logn = logn;
+            g_cache.fingerprint = fp;
+        }
+        g_cache.prover->prove(circuit, &proof);
+        if (!use_cache) {
+            delete g_cache.prover;
+            g_cache.prover = nullptr;
+        }
+    } catch (const std::exception& e) {
+        // the reference prints and exits on any CUDA failure (lib/caffe/common.hpp:23-30)
+        fprintf(stderr, "libzprize_b200: gen_proof failed: %s\n", e.what());
+        exit(EXIT_FAILURE);
+    }
+    return proof;
+}
+
+// ---- operator entry points ---------------------------------------------------------------------
+int zp_ntt_host(zp_prover* p, int kind, int log_n, const uint64_t* in, uint64_t* out) {
+    return guard([&] {
+        Prover* pr = P(p);
+        size_t n = (size_t)1 << log_n;
+        DevBuf<fr_t> a(n), b(n);
+        ZP_CUDA(cudaMemcpyAsync(a.p, in, n * sizeof(fr_t), cudaMemcpyHostToDevice, pr->st));
+        ntt_run(pr->T, pr->NS, (NttKind)kind, log_n, a.p, n, b.p, pr->st);
+        ZP_CUDA(cudaMemcpyAsync(out, b.p, n * sizeof(fr_t), cudaMemcpyDeviceToHost, pr->st));
+        ZP_CUDA(cudaStreamSynchronize(pr->st));
+    });
+}
+static void msm_to_affine_out(const host::G1& r, uint64_t* out) {
+    host::Fq x, y;
+    bool inf;
+    r.to_affine(x, y, inf);
+    memcpy(out, x.v, 48);
+    memcpy(out + 6, y.v, 48);
+}
+int zp_msm_host(zp_prover* p, const uint64_t* scalars, size_t n, uint64_t* out_affine) {
+    return guard([&] {
+        Prover* pr = P(p);
+        if (n > pr->srs.n) throw std::runtime_error("zp_msm_host: more scalars than resident SRS points");
+        DevBuf<fr_t> s(n);
+        ZP_CUDA(cudaMemcpyAsync(s.p, scalars, n * sizeof(fr_t), cudaMemcpyHostToDevice, pr->st));
+        MsmConfig cfg = msm_config_for(n);
+        msm_launch(pr->MW, cfg, pr->srs.p, s.p, n, pr->st);
+        msm_to_affine_out(msm_collect(pr->MW, cfg, pr->st), out_affine);
+    });
+}
+int zp_msm_points_host(zp_prover* p, const uint64_t* points, const uint64_t* scalars, size_t n, int window_bits,
+                       uint64_t* out_affine) {
+    return guard([&] {
+        Prover* pr = P(p);
+        DevBuf<fr_t> s(n);
+        DevBuf<affine_t> pts(n);
+        ZP_CUDA(cudaMemcpyAsync(s.p, scalars, n * sizeof(fr_t), cudaMemcpyHostToDevice, pr->st));
+        ZP_CUDA(cudaMemcpyAsync(pts.p, points, n * sizeof(affine_t), cudaMemcpyHostToDevice, pr->st));
+        MsmConfig cfg = msm_config_for(n, window_bits);
+        msm_launch(pr->MW, cfg, pts.p, s.p, n, pr->st);
+        msm_to_affine_out(msm_collect(pr->MW, cfg, pr->st), out_affine);
+    });
+}
+int zp_poly_eval_host(zp_prover* p, const uint64_t* coeffs, size_t n, const uint64_t* point, uint64_t* out) {
+    return guard([&] {
+        Prover* pr = P(p);
+        DevBuf<fr_t> a(n);
+        ZP_CUDA(cudaMemcpyAsync(a.p, coeffs, n * sizeof(fr_t), cudaMemcpyHostToDevice, pr->st));
+        const fr_t* polys[1] = {a.p};
+        fr_t pt, res;
+        memcpy(pt.l, point, 32);
+        evaluate_many(pr->PS, polys, &pt, 1, n, &res, pr->st);
+        memcpy(out, res.l, 32);
+    });
+}
+int zp_poly_divide_host(zp_prover* p, const uint64_t* coeffs, size_t n, const uint64_t* point, uint64_t* out) {
+    return guard([&] {
+        Prover* pr = P(p);
+        DevBuf<fr_t> a(n), q(n);
+        ZP_CUDA(cudaMemcpyAsync(a.p, coeffs, n * sizeof(fr_t), cudaMemcpyHostToDevice, pr->st));
+        fr_t pt;
+        memcpy(pt.l, point, 32);
+        divide_by_linear(pr->PS, a.p, n, pt, q.p, pr->st);
+        ZP_CUDA(cudaMemcpyAsync(out, q.p, (n - 1) * sizeof(fr_t), cudaMemcpyDeviceToHost, pr->st));
+        ZP_CUDA(cudaStreamSynchronize(pr->st));
+    });
+}
+int zp_prefix_product_host(zp_prover* p, const uint64_t* in, size_t n, uint64_t* out) {
+    return guard([&] {
+        Prover* pr = P(p);
+        DevBuf<fr_t> a(n), b(n);
+        ZP_CUDA(cudaMemcpyAsync(a.p, in, n * sizeof(fr_t), cudaMemcpyHostToDevice, pr->st));
+        exclusive_prefix_product(pr->PS, a.p, b.p, n, pr->st);
+        ZP_CUDA(cudaMemcpyAsync(out, b.p, n * sizeof(fr_t), cudaMemcpyDeviceToHost, pr->st));
+        ZP_CUDA(cudaStreamSynchronize(pr->st));
+    });
+}
+
+// ---- device-resident benchmark helpers ---------------------------------------------------------
+int zp_bench_alloc(zp_prover* p, int slot, size_t n_fr) {
+    return guard([&] {
+        if (slot < 0 || slot >= 8) throw std::runtime_error("zp_bench_alloc: slot out of range");
+        bench_of(p).slot[slot].alloc(n_fr);
+    });
+}
+int zp_bench_upload(zp_prover* p, int slot, const uint64_t* host, size_t n_fr) {
+    return guard([&] {
+        BenchState& b = bench_of(p);
+        if (slot < 0 || slot >= 8 || b.slot[slot].n < n_fr) throw std::runtime_error("zp_bench_upload: bad slot");
+        ZP_CUDA(cudaMemcpy(b.slot[slot].p, host, n_fr * sizeof(fr_t), cudaMemcpyHostToDevice));
+    });
+}
+int zp_bench_download(zp_prover* p, int slot, uint64_t* host, size_t n_fr) {
+    return guard([&] {
+        BenchState& b = bench_of(p);
+        if (slot < 0 || slot >= 8 || b.slot[slot].n < n_fr) throw std::runtime_error("zp_bench_download: bad slot");
+        ZP_CUDA(cudaMemcpy(host, b.slot[slot].p, n_fr * sizeof(fr_t), cudaMemcpyDeviceToHost));
+    });
+}
+int zp_bench_ntt(zp_prover* p, int kind, int log_n, int slot_in, int slot_out, int iters, double* ms) {
+    return guard([&] {
+        Prover* pr = P(p);
+        BenchState& b = bench_of(p);
+        size_t n = (size_t)1 << log_n;
+        if (b.slot[slot_in].n < n || b.slot[slot_out].n < n) throw std::runtime_error("zp_bench_ntt: slots too small");
+        cudaEvent_t e0, e1;
+        ZP_CUDA(cudaEventCreate(&e0));
+        ZP_CUDA(cudaEventCreate(&e1));
+        ZP_CUDA(cudaEventRecord(e0, pr->st));
+        for (int i = 0; i < iters; i++) ntt_run(pr->T, pr->NS, (NttKind)kind, log_n, b.slot[slot_in].p, n, b.slot[slot_out].p, pr->st);
+        ZP_CUDA(cudaEventRecord(e1, pr->st));
+        ZP_CUDA(cudaEventSynchronize(e1));
+        float t = 0;
+        ZP_CUDA(cudaEventElapsedTime(&t, e0, e1));
+        *ms = t / iters;
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    });
+}
+int zp_bench_msm(zp_prover* p, int slot, size_t n, int iters, double* ms, uint64_t* out_affine) {
+    return guard([&] {
+        Prover* pr = P(p);
+        BenchState& b = bench_of(p);
+        if (b.slot[slot].n < n || pr->srs.n < n) throw std::runtime_error("zp_bench_msm: slot or SRS too small");
+        MsmConfig cfg = msm_config_for(n);
+        cudaEvent_t e0, e1;
+        ZP_CUDA(cudaEventCreate(&e0));
+        ZP_CUDA(cudaEventCreate(&e1));
+        host::G1 r = host::G1::infinity();
+        pr->MW.timing = true;
+        ZP_CUDA(cudaEventRecord(e0, pr->st));
+        for (int i = 0; i < iters; i++) {
+            msm_launch(pr->MW, cfg, pr->srs.p, b.slot[slot].p, n, pr->st);
+            r = msm_collect(pr->MW, cfg, pr->st);
+        }
+        ZP_CUDA(cudaEventRecord(e1, pr->st));
+        ZP_CUDA(cudaEventSynchronize(e1));
+        float t = 0;
+        ZP_CUDA(cudaEventElapsedTime(&t, e0, e1));
+        *ms = t / iters;
+        if (out_affine) msm_to_affine_out(r, out_affine);
+        pr->MW.timing = false;
+        for (int k = 0; k < 5; k++) b.msm_ms[k] = pr->MW.last_ms[k];
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    });
+}
+int zp_bench_msm_breakdown(zp_prover* p, double* ms5) {
+    return guard([&] {
+        for (int k = 0; k < 5; k++) ms5[k] = bench_of(p).msm_ms[k];
+    });
+}
+
+}  // extern "C"
+
+// ---- integer-pipe microbenchmark ("measure with a dependent-free mad.lo.u32 microbenchmark")
+__global__ void int_pipe_kernel(int mode, int iters, uint32_t* sink) {
+    uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (mode == 0) {
+        uint32_t a0 = tid, a1 = tid + 1, a2 = tid + 2, a3 = tid + 3, a4 = tid + 4, a5 = tid + 5, a6 = tid + 6, a7 = tid + 7;
+        uint32_t m = tid | 1u;
+        for (int i = 0; i < iters; i++) {
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                a0 = a0 * m + a1; a1 = a1 * m + a2; a2 = a2 * m + a3; a3 = a3 * m + a4;
+                a4 = a4 * m + a5; a5 = a5 * m + a6; a6 = a6 * m + a7; a7 = a7 * m + a0;
+            }
+        }
+        sink[tid] = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+    } else if (mode == 1) {
+        unsigned long long a0 = tid, a1 = tid + 1, a2 = tid + 2, a3 = tid + 3, a4 = tid + 4, a5 = tid + 5, a6 = tid + 6, a7 = tid + 7;
+        uint32_t m = tid | 1u;
+        for (int i = 0; i < iters; i++) {
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                a0 = (unsigned long long)(uint32_t)a0 * m + a1; a1 = (unsigned long long)(uint32_t)a1 * m + a2;
+                a2 = (unsigned long long)(uint32_t)a2 * m + a3; a3 = (unsigned long long)(uint32_t)a3 * m + a4;
+                a4 = (unsigned long long)(uint32_t)a4 * m + a5; a5 = (unsigned long long)(uint32_t)a5 * m + a6;
+                a6 = (unsigned long long)(uint32_t)a6 * m + a7; a7 = (unsigned long long)(uint32_t)a7 * m + a0;
+            }
+        }
+        sink[tid] = (uint32_t)(a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7);
+    } else {
+        fq_t x = fq_t::one(), y = fq_t::rr();
+        x.l[0] ^= tid;
+        y.l[1] ^= tid;
+        for (int i = 0; i < iters; i++) {
+            x = x * y;
+            y = y * x;
+        }
+        sink[tid] = x.l[0] ^ y.l[3];
+    }
+}
+
+extern "C" int zp_bench_int_pipe(zp_prover* p, int mode, double* gops) {
+    return guard([&] {
+        Prover* pr = P(p);
+        const int blocks = 148 * 8, threads = 256;
+        DevBuf<uint32_t> sink((size_t)blocks * threads);
+        int iters = mode == 2 ? 200 : 2000;
+        cudaEvent_t e0, e1;
+        ZP_CUDA(cudaEventCreate(&e0));
+        ZP_CUDA(cudaEventCreate(&e1));
+        ZP_LAUNCH(int_pipe_kernel, dim3(blocks), dim3(threads), 0, pr->st, mode, 10, sink.p);
+        ZP_CUDA(cudaEventRecord(e0, pr->st));
+        ZP_LAUNCH(int_pipe_kernel, dim3(blocks), dim3(threads), 0, pr->st, mode, iters, sink.p);
+        ZP_CUDA(cudaEventRecord(e1, pr->st));
+        ZP_CUDA(cudaEventSynchronize(e1));
+        float t = 0;
+        ZP_CUDA(cudaEventElapsedTime(&t, e0, e1));
+        double ops = (double)blocks * threads * iters * (mode == 2 ? 2.0 : 64.0);
+        *gops = ops / (t * 1e-3) / 1e9;
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    });
+}

@@ -1,0 +1,42 @@
+// G1 multi-scalar multiplication (KZG commitments).  Host-side interface of msm.cu.
+// Replaces the reference's `multi_scalar_mult` ("Prize 1B/plonk-core/lib/PLONK/utils/function.cu":275-290
+// -> "…/utils/zkp/cuda/zksnark_msm.cu":45-83 -> sppark pippenger.cuh:470-556 -> CPU collect.h:378-445).
+#pragma once
+#include "common.cuh"
+#include "curve.cuh"
+#include "host_math.hpp"
+
+namespace zp {
+
+struct MsmConfig {
+    int c;        // window bits
+    int nwin;     // number of windows = ceil(256 / c)
+    int nbuckets; // per window = 2^(c-1)
+};
+MsmConfig msm_config_for(size_t n, int c_override = 0);
+
+struct MsmWorkspace {
+    DevBuf<uint32_t> digits;   // [nwin][n]   |d| | sign << 31
+    DevBuf<uint32_t> sorted;   // [<= nwin*n] point index | sign << 31, grouped by (window, bucket)
+    DevBuf<uint32_t> start;    // [nwin*nbuckets + 1] exclusive scan of bucket sizes
+    DevBuf<uint32_t> cursor;   // [nwin*nbuckets]     running insert position; == bucket end after the scatter
+    DevBuf<xyzz_t> buckets;    // [nwin*nbuckets]
+    DevBuf<xyzz_t> partial;    // [nwin * MSM_REDUCE_GROUPS]
+    std::vector<xyzz_t> partial_host;
+    // optional per-kernel timing (bench only): digits, scan, scatter, accumulate, reduce
+    bool timing = false;
+    cudaEvent_t ev[6] = {0, 0, 0, 0, 0, 0};
+    double last_ms[5] = {0, 0, 0, 0, 0};
+    void reserve(size_t n, const MsmConfig& cfg);
+};
+static const int MSM_REDUCE_GROUPS = 8;
+
+// result = sum_i scalars[i] * points[i]; scalars are Montgomery Fr (as they live in polynomial buffers;
+// the canonical conversion the reference does as a separate `to_base` pass is fused into the digit kernel).
+// Returns the partial sums per window on the host; msm_finish() folds them into one point.
+// When `shard_lo/shard_hi` restrict the point range, the result is that range's partial sum (multi-GPU).
+void msm_launch(MsmWorkspace& ws, const MsmConfig& cfg, const affine_t* points, const fr_t* scalars, size_t n,
+                cudaStream_t st);
+host::G1 msm_collect(MsmWorkspace& ws, const MsmConfig& cfg, cudaStream_t st);
+
+}  // namespace zp

@@ -1,0 +1,256 @@
+// Fr NTT family for sm_100a — see ntt.cuh for the contract and DESIGN.md §NTT for the derivation.
+//
+// Decomposition: N = R_0 R_1 … R_{P-1} (R_p = 2^{lr_p}, lr_p <= 9).  Before pass p the array is the
+// tensor [n_p][n_{p+1}]…[n_{P-1}][k_{p-1}]…[k_0] (row-major, leftmost slowest); pass p transforms the
+// leading digit n_p -> k_p and writes [n_{p+1}]…[n_{P-1}][k_p][k_{p-1}]…[k_0].  p = 0 is the natural
+// input order, after the last pass the layout is [k_{P-1}]…[k_0] = natural output order: no separate
+// bit-reversal pass, no separate coset-power pass, no separate 1/N pass, zero padding is implicit.
+// Each CTA owns a tile of R_p x C elements (C consecutive values of the flattened trailing index q), so
+// every global read is a C*32-byte contiguous segment and every write a >= C*32-byte one.
+// Inside the tile the size-R_p transforms run as radix-2 DIF stages in shared memory (output index read
+// back bit-reversed).  The inter-pass twiddle  omega_N^{n_p * S_p * K_{p-1}}  is applied on load.
+#include "ntt.cuh"
+
+namespace zp {
+
+// TWO_ADIC_ROOT_OF_UNITY and multiplicative generator 7 of BLS12-381 Fr, Montgomery form
+// (same values as "Prize 1B/plonk-core/lib/PLONK/src/bls12_381/fr.cuh":39-53).
+fr_t fr_two_adic_root_host() {
+    fr_t r;
+    const uint64_t v[4] = {13381757501831005802ULL, 6564924994866501612ULL, 789602057691799140ULL, 6625830629041353339ULL};
+    memcpy(r.l, v, 32);
+    return r;
+}
+fr_t fr_generator_host() {
+    fr_t r;
+    const uint64_t v[4] = {64424509425ULL, 1721329240476523535ULL, 18418692815241631664ULL, 3824455624000121028ULL};
+    memcpy(r.l, v, 32);
+    return r;
+}
+
+// table[i] = base^(i << shift)
+__global__ void power_table_kernel(fr_t* table, fr_t base, int shift, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t e = (uint64_t)i << shift;
+    store_fr(&table[i], base.pow_u64(e));
+}
+
+void NttTables::init(cudaStream_t st) {
+    if (ready) return;
+    fr_t w = fr_two_adic_root_host();  // order 2^32
+    for (int i = NTT_LMAX; i < 32; i++) w = w.sqr();
+    omega[NTT_LMAX] = w;
+    for (int k = NTT_LMAX - 1; k >= 0; k--) omega[k] = omega[k + 1].sqr();
+    fr_t two_inv = fr_t::from_u32(2).inverse();
+    ninv[0] = fr_t::one();
+    for (int k = 1; k <= NTT_LMAX; k++) ninv[k] = ninv[k - 1] * two_inv;
+    for (int k = 0; k <= NTT_LMAX; k++) omega_inv[k] = omega[k].inverse();
+    const int LO = 1 << NTT_LO_BITS, HI = 1 << (NTT_LMAX - NTT_LO_BITS);
+    w_lo.alloc(LO); w_hi.alloc(HI);
+    g_lo.alloc(LO); g_hi.alloc(HI);
+    gi_lo.alloc(LO); gi_hi.alloc(HI);
+    fr_t g = fr_generator_host(), gi = g.inverse();
+    ZP_LAUNCH(power_table_kernel, dim3((LO + 255) / 256), dim3(256), 0, st, w_lo.p, omega[NTT_LMAX], 0, LO);
+    ZP_LAUNCH(power_table_kernel, dim3((HI + 255) / 256), dim3(256), 0, st, w_hi.p, omega[NTT_LMAX], NTT_LO_BITS, HI);
+    ZP_LAUNCH(power_table_kernel, dim3((LO + 255) / 256), dim3(256), 0, st, g_lo.p, g, 0, LO);
+    ZP_LAUNCH(power_table_kernel, dim3((HI + 255) / 256), dim3(256), 0, st, g_hi.p, g, NTT_LO_BITS, HI);
+    ZP_LAUNCH(power_table_kernel, dim3((LO + 255) / 256), dim3(256), 0, st, gi_lo.p, gi, 0, LO);
+    ZP_LAUNCH(power_table_kernel, dim3((HI + 255) / 256), dim3(256), 0, st, gi_hi.p, gi, NTT_LO_BITS, HI);
+    ready = true;
+}
+
+struct NttPassParams {
+    int logn;       // log2 N
+    int lr;         // log2 R_p
+    int lc;         // log2 C (tile width)
+    int lk;         // log2 K_done = lr_0 + … + lr_{p-1}
+    int first, last;
+    int inverse;    // use omega^-1
+    int coset;      // 0 none, 1 multiply input by g^n (first pass), 2 multiply output by g^-k (last pass)
+    size_t n_in;    // elements >= n_in of the input are implicit zeros (first pass only)
+    const fr_t *w_lo, *w_hi, *c_lo, *c_hi;
+    fr_t ninv;      // 2^-logn (used when inverse && last)
+};
+
+// omega_{2^LMAX}^e, e in [0, 2^LMAX)
+ZP_D fr_t tw_lookup(const fr_t* lo_t, const fr_t* hi_t, uint32_t e) {
+    uint32_t lo = e & ((1u << NTT_LO_BITS) - 1), hi = e >> NTT_LO_BITS;
+    if (lo == 0) return load_fr(&hi_t[hi]);
+    fr_t a = load_fr(&lo_t[lo]);
+    if (hi == 0) return a;
+    return a * load_fr(&hi_t[hi]);
+}
+
+ZP_D void sm_store(uint4* sm, int half_stride, int idx, const fr_t& v) {
+    sm[idx] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    sm[half_stride + idx] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+ZP_D fr_t sm_load(const uint4* sm, int half_stride, int idx) {
+    uint4 a = sm[idx], b = sm[half_stride + idx];
+    fr_t r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+
+__global__ void __launch_bounds__(512) ntt_pass_kernel(const fr_t* __restrict__ in, fr_t* __restrict__ out, NttPassParams p) {
+    ZP_DYN_SMEM(uint4, sm);
+    const int R = 1 << p.lr, C = 1 << p.lc, RC = R * C;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const size_t q0 = (size_t)blockIdx.x << p.lc;
+    const uint32_t emask = (1u << NTT_LMAX) - 1;
+
+    // ---- load tile [n][c], applying coset powers / inter-pass twiddles
+    for (int e = tid; e < RC; e += nt) {
+        int n = e >> p.lc, c = e & (C - 1);
+        size_t q = q0 + c;
+        size_t pos = ((size_t)n << (p.logn - p.lr)) + q;
+        fr_t v;
+        bool nz = true;
+        if (p.first) {
+            nz = pos < p.n_in;
+            v = nz ? load_fr(&in[pos]) : fr_t::zero();
+            if (nz && p.coset == 1 && pos != 0) {
+                uint32_t lo = (uint32_t)pos & ((1u << NTT_LO_BITS) - 1), hi = (uint32_t)(pos >> NTT_LO_BITS);
+                fr_t f = load_fr(&p.c_lo[lo]);
+                if (hi) f = f * load_fr(&p.c_hi[hi]);
+                v = v * f;
+            }
+        } else {
+            v = load_fr(&in[pos]);
+            uint32_t ks = (uint32_t)q & ((1u << p.lk) - 1);
+            uint32_t ex = ((uint32_t)n * ks) << (NTT_LMAX - (p.lk + p.lr));  // theta = omega_{T_{p+1}}
+            if (ex) {
+                if (p.inverse) ex = ((1u << NTT_LMAX) - ex) & emask;
+                v = v * tw_lookup(p.w_lo, p.w_hi, ex);
+            }
+        }
+        sm_store(sm, RC, e, v);
+    }
+    __syncthreads();
+
+    // ---- radix-2 DIF stages over n (in place, result index bit-reversed)
+    const int nb = RC >> 1;
+    for (int s = 0; s < p.lr; s++) {
+        const int lhalf = p.lr - 1 - s;
+        const int half = 1 << lhalf;
+        for (int b = tid; b < nb; b += nt) {
+            int c = b & (C - 1), t = b >> p.lc;
+            int j = t & (half - 1), blk = t >> lhalf;
+            int i0 = ((blk << (lhalf + 1)) + j) * C + c, i1 = i0 + half * C;
+            fr_t u = sm_load(sm, RC, i0), v = sm_load(sm, RC, i1);
+            sm_store(sm, RC, i0, u + v);
+            fr_t d = u - v;
+            if (j) {
+                uint32_t ex = ((uint32_t)j << s) << (NTT_LMAX - p.lr);
+                if (p.inverse) ex = ((1u << NTT_LMAX) - ex) & emask;
+                d = d * tw_lookup(p.w_lo, p.w_hi, ex);
+            }
+            sm_store(sm, RC, i1, d);
+        }
+        __syncthreads();
+    }
+
+    // ---- store: X[k] sits at bit-reversed row
+    const int sh = 32 - p.lr;
+    for (int e = tid; e < RC; e += nt) {
+        int k, c;
+        size_t pos;
+        if (p.first) {  // K_done = 1: whole tile is one contiguous block [c][k]
+            k = e & (R - 1);
+            c = e >> p.lr;
+            pos = (q0 << p.lr) + e;
+        } else {
+            k = e >> p.lc;
+            c = e & (C - 1);
+            size_t q = q0 + c;
+            size_t rest = q >> p.lk, ks = q & (((size_t)1 << p.lk) - 1);
+            pos = (rest << (p.lk + p.lr)) + ((size_t)k << p.lk) + ks;
+        }
+        int row = p.lr ? (int)(__brev((uint32_t)k) >> sh) : 0;
+        fr_t v = sm_load(sm, RC, row * C + c);
+        if (p.last) {
+            if (p.coset == 2) {
+                uint32_t lo = (uint32_t)pos & ((1u << NTT_LO_BITS) - 1), hi = (uint32_t)(pos >> NTT_LO_BITS);
+                fr_t f = p.ninv;
+                if (lo) f = f * load_fr(&p.c_lo[lo]);
+                if (hi) f = f * load_fr(&p.c_hi[hi]);
+                v = v * f;
+            } else if (p.inverse) {
+                v = v * p.ninv;
+            }
+        }
+        store_fr(&out[pos], v);
+    }
+}
+
+void ntt_run(const NttTables& T, NttScratch& S, NttKind kind, int logn, const fr_t* in, size_t n_in, fr_t* out,
+             cudaStream_t st) {
+    if (logn > NTT_LMAX) throw std::runtime_error("ntt_run: domain larger than 2^26");
+    const size_t N = (size_t)1 << logn;
+    if (n_in > N) n_in = N;
+    if (logn == 0) {
+        if (n_in) ZP_CUDA(cudaMemcpyAsync(out, in, sizeof(fr_t), cudaMemcpyDeviceToDevice, st));
+        else ZP_CUDA(cudaMemsetAsync(out, 0, sizeof(fr_t), st));
+        return;
+    }
+    const int KMAX = 9;
+    int P = (logn + KMAX - 1) / KMAX;
+    int bits[8];
+    for (int p = 0; p < P; p++) bits[p] = logn / P + (p < logn % P ? 1 : 0);
+    bool inverse = (kind == NTT_INV || kind == NTT_COSET_INV);
+    if (P > 1) S.reserve(N);
+    const fr_t* src = in;
+    int lk = 0;
+    for (int p = 0; p < P; p++) {
+        bool last = (p == P - 1);
+        fr_t* dst;
+        if (last) {
+            dst = out;
+            if (dst == src) {  // single pass, in == out: go through scratch
+                S.reserve(N);
+                dst = S.s1.p;
+            }
+        } else {
+            dst = (p & 1) ? S.s2.p : S.s1.p;
+        }
+        NttPassParams pp;
+        pp.logn = logn;
+        pp.lr = bits[p];
+        int lq = logn - bits[p];  // log2 of number of q values
+        int lc = 12 - bits[p];     // tile of 4096 elements (128 KiB of shared memory)
+        if (lc > lq) lc = lq;
+        if (p > 0 && lc > lk) lc = lk;  // C must divide K_done
+        if (lc < 0) lc = 0;
+        pp.lc = lc;
+        pp.lk = lk;
+        pp.first = (p == 0);
+        pp.last = last;
+        pp.inverse = inverse;
+        pp.coset = (kind == NTT_COSET_FWD) ? 1 : (kind == NTT_COSET_INV ? 2 : 0);
+        pp.n_in = n_in;
+        pp.w_lo = T.w_lo.p;
+        pp.w_hi = T.w_hi.p;
+        pp.c_lo = (kind == NTT_COSET_FWD) ? T.g_lo.p : T.gi_lo.p;
+        pp.c_hi = (kind == NTT_COSET_FWD) ? T.g_hi.p : T.gi_hi.p;
+        pp.ninv = T.ninv[logn];
+        int RC = 1 << (pp.lr + pp.lc);
+        size_t smem = (size_t)RC * 32;
+        int threads = RC / 2 < 512 ? (RC / 2 < 32 ? 32 : RC / 2) : 512;
+        unsigned grid = (unsigned)(((size_t)1 << lq) >> lc);
+#ifndef ZP_EMU
+        static bool attr_set = false;
+        if (!attr_set) {
+            ZP_CUDA(cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+            attr_set = true;
+        }
+#endif
+        ZP_LAUNCH(ntt_pass_kernel, dim3(grid), dim3(threads), smem, st, src, dst, pp);
+        if (last && dst != out) ZP_CUDA(cudaMemcpyAsync(out, dst, N * sizeof(fr_t), cudaMemcpyDeviceToDevice, st));
+        src = dst;
+        lk += bits[p];
+    }
+}
+
+}  // namespace zp

@@ -1,0 +1,45 @@
+// Fr NTT / iNTT / coset-NTT / coset-iNTT, natural order in and out.
+// Host-side interface of ntt.cu.  Replaces the reference's `Ntt/Intt/Ntt_coset/Intt_coset::forward`
+// ("Prize 1B/plonk-core/lib/PLONK/utils/function.cu":249-273 -> "…/utils/zkp/cuda/zksnark_ntt.cu":16-92
+// -> sppark `_CT_NTT`, `bit_rev_permutation`, `LDE_distribute_powers`); semantics of ark-poly 0.3
+// `GeneralEvaluationDomain::{fft, ifft, coset_fft, coset_ifft}`.
+#pragma once
+#include "common.cuh"
+
+namespace zp {
+
+enum NttKind { NTT_FWD = 0, NTT_INV = 1, NTT_COSET_FWD = 2, NTT_COSET_INV = 3 };
+
+static const int NTT_LMAX = 26;      // largest supported log2 domain (2^25 = 8N at HEIGHT=15)
+static const int NTT_LO_BITS = 13;   // two-level power tables: x^e = hi[e >> 13] * lo[e & 8191]
+
+struct NttTables {
+    // all tables resident for the life of the context (built once, not per transform object as the
+    // reference does 9 times per proof — SURVEY §2.3 `generate_*_twiddles`)
+    DevBuf<fr_t> w_lo, w_hi;        // omega_{2^LMAX}^e
+    DevBuf<fr_t> g_lo, g_hi;        // 7^e
+    DevBuf<fr_t> gi_lo, gi_hi;      // 7^-e
+    fr_t ninv[NTT_LMAX + 1];        // 2^-k (host copies, passed by value to kernels)
+    fr_t omega[NTT_LMAX + 1];       // primitive 2^k-th roots (host)
+    fr_t omega_inv[NTT_LMAX + 1];
+    bool ready = false;
+    void init(cudaStream_t st);
+};
+
+struct NttScratch {
+    DevBuf<fr_t> s1, s2;
+    void reserve(size_t n) {
+        if (s1.n < n) s1.alloc(n);
+        if (s2.n < n) s2.alloc(n);
+    }
+};
+
+// out[0..2^logn) = transform(in[0..n_in) zero-padded to 2^logn).  in == out is allowed.
+void ntt_run(const NttTables& T, NttScratch& S, NttKind kind, int logn, const fr_t* in, size_t n_in, fr_t* out,
+             cudaStream_t st);
+
+// host-side field helpers shared by the driver
+fr_t fr_two_adic_root_host();
+fr_t fr_generator_host();
+
+}  // namespace zp

@@ -1,0 +1,707 @@
+// gen_proof protocol driver: the five PLONK rounds of `Prover::prove_with_preprocessed`
+// ("Prize 1B/plonk-core/src/proof_system/prover.rs":171-660; PNP's GPU twin
+// "Prize 1B/plonk-core/lib/PLONK/src/gen_proof.cuh":10-489) on top of the resident context.
+// Transcript schedule = SURVEY Appendix A.  Everything heavy stays in HBM; per proof only the witness
+// columns go host->device and 19 points + 26 scalars come back.
+#include "prover.cuh"
+#include "gates.cuh"
+#include <algorithm>
+#include <unordered_map>
+
+namespace zp {
+
+unsigned long long g_launch_count = 0;
+
+using host::Fr;
+using host::Fq;
+
+// ---- phase timing with CUDA events on the prover's stream ----------------------------------------
+struct PhaseTimer {
+    struct Span { int cat; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> pool;
+    size_t used = 0;
+    cudaStream_t st;
+    explicit PhaseTimer(cudaStream_t s) : st(s) {}
+    ~PhaseTimer() { for (auto e : pool) cudaEventDestroy(e); }
+    cudaEvent_t get() {
+        if (used == pool.size()) {
+            cudaEvent_t e;
+            ZP_CUDA(cudaEventCreate(&e));
+            pool.push_back(e);
+        }
+        return pool[used++];
+    }
+    void reset() { spans.clear(); used = 0; }
+    int begin(int cat) {
+        Span s;
+        s.cat = cat;
+        s.a = get();
+        s.b = get();
+        ZP_CUDA(cudaEventRecord(s.a, st));
+        spans.push_back(s);
+        return (int)spans.size() - 1;
+    }
+    void end(int id) { ZP_CUDA(cudaEventRecord(spans[id].b, st)); }
+    void collect(double* out5) {
+        ZP_CUDA(cudaStreamSynchronize(st));
+        for (int i = 0; i < 5; i++) out5[i] = 0;
+        for (auto& s : spans) {
+            float ms = 0;
+            ZP_CUDA(cudaEventElapsedTime(&ms, s.a, s.b));
+            out5[s.cat] += ms;
+        }
+    }
+};
+enum { CAT_TOTAL = 0, CAT_NTT = 1, CAT_MSM = 2, CAT_QUOT = 3, CAT_OTHER = 4 };
+static PhaseTimer* g_timer = nullptr;
+struct Scope {
+    int id;
+    explicit Scope(int cat) : id(g_timer ? g_timer->begin(cat) : -1) {}
+    ~Scope() { if (g_timer && id >= 0) g_timer->end(id); }
+};
+
+// ---- context -----------------------------------------------------------------------------------
+Prover::Prover(int logn_) : logn(logn_), n((size_t)1 << logn_), n8((size_t)8 << logn_) {
+    if (logn < 6 || logn + 3 > NTT_LMAX) throw std::runtime_error("zp_prover_create: log_n must be in [6, 23]");
+    ZP_CUDA(cudaStreamCreate(&st));
+    T.init(st);
+    PS.init();
+    // L_1 on the coset: coefficients are all 1/N (quotient_poly.rs:346-358)
+    l1_coset.alloc(n8);
+    DevBuf<fr_t> tmp(n);
+    fill(tmp.p, T.ninv[logn], n, st);
+    ntt_run(T, NS, NTT_COSET_FWD, logn + 3, tmp.p, n, l1_coset.p, st);
+    ZP_CUDA(cudaStreamSynchronize(st));
+}
+Prover::~Prover() {
+    if (st) cudaStreamDestroy(st);
+}
+
+void Prover::ensure_work_buffers(bool lookup) {
+    auto need = [](DevBuf<fr_t>& b, size_t cnt) { if (b.n < cnt) b.alloc(cnt); };
+    for (int k = 0; k < 4; k++) {
+        need(w_ev[k], n);
+        need(w_poly[k], n);
+        need(w8[k], n8);
+    }
+    need(qlk_ev, n);
+    need(z_poly, n);
+    need(z8, n8);
+    need(z2_poly, n);
+    need(pi_poly, n);
+    need(pi8, n8);
+    need(quot, n8);
+    need(t_poly, n8);
+    need(num, n);
+    need(den, n);
+    need(lin, n);
+    need(comb, n);
+    need(wit, n);
+    if (lookup) {
+        need(z28, n8);
+        need(t_ev, n); need(f_ev, n); need(h1_ev, n); need(h2_ev, n);
+        need(table_poly, n); need(f_poly, n); need(h1_poly, n); need(h2_poly, n);
+        need(tb8, n8); need(f8, n8); need(h18, n8); need(h28, n8);
+    }
+}
+
+void Prover::load_srs(const uint64_t* pts, size_t npts) {
+    if (npts < n) throw std::runtime_error("zp_prover_load_srs: fewer than N points");
+    srs.alloc(n);  // only the first N powers are ever used (load.cu:348-351)
+    ZP_CUDA(cudaMemcpyAsync(srs.p, pts, n * sizeof(affine_t), cudaMemcpyHostToDevice, st));
+    ZP_CUDA(cudaStreamSynchronize(st));
+}
+
+// ---- insecure SRS generation (test / benchmark harness; the reference calls KZG10::setup in Rust) ----
+__global__ void srs_power_table_kernel(fr_t* table, fr_t base, int shift, int cnt) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cnt) return;
+    store_fr(&table[i], base.pow_u64((uint64_t)i << shift));
+}
+__global__ void __launch_bounds__(128) srs_kernel(affine_t* out, size_t cnt, const fr_t* pw_lo, const fr_t* pw_hi,
+                                                  const affine_t* pow2) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cnt) return;
+    fr_t s = load_fr(&pw_lo[i & 8191]);
+    if (i >> 13) s = s * load_fr(&pw_hi[i >> 13]);
+    s = s.from_mont();
+    xyzz_t acc = xyzz_t::infinity();
+    for (int j = 0; j < 255; j++) {
+        if ((s.l[j >> 5] >> (j & 31)) & 1) {
+            fq_t x = load_fq(&pow2[j].x), y = load_fq(&pow2[j].y);
+            acc.add_affine(x, y);
+        }
+    }
+    // tau^i != 0, so acc is finite
+    fq_t inv = (acc.ZZ * acc.ZZZ).inverse();
+    fq_t zz_inv = inv * acc.ZZZ, zzz_inv = inv * acc.ZZ;
+    store_fq(&out[i].x, acc.X * zz_inv);
+    store_fq(&out[i].y, acc.Y * zzz_inv);
+}
+static void g1_generator_host(Fq& x, Fq& y) {
+    // standard BLS12-381 G1 generator, canonical big-endian hex -> Montgomery
+    static const uint64_t gx[6] = {0xfb3af00adb22c6bbULL, 0x6c55e83ff97a1aefULL, 0xa14e3a3f171bac58ULL,
+                                   0xc3688c4f9774b905ULL, 0x2695638c4fa9ac0fULL, 0x17f1d3a73197d794ULL};
+    static const uint64_t gy[6] = {0x0caa232946c5e7e1ULL, 0xd03cc744a2888ae4ULL, 0x00db18cb2c04b3edULL,
+                                   0xfcf5e095d5d00af6ULL, 0xa09e30ed741d8ae4ULL, 0x08b3f481e3aaa0f1ULL};
+    x = Fq::from_canonical(gx);
+    y = Fq::from_canonical(gy);
+}
+void Prover::generate_srs(const fr_t& tau, size_t npts) {
+    if (npts < n) throw std::runtime_error("zp_prover_generate_srs: fewer than N points");
+    npts = n;
+    std::vector<affine_t> pow2(255);
+    Fq gx, gy;
+    g1_generator_host(gx, gy);
+    host::G1 p = host::G1::from_affine(gx, gy);
+    for (int j = 0; j < 255; j++) {
+        Fq ax, ay;
+        bool inf;
+        p.to_affine(ax, ay, inf);
+        pow2[j].x = host::to_dev(ax);
+        pow2[j].y = host::to_dev(ay);
+        p.dbl_inplace();
+    }
+    DevBuf<affine_t> d_pow2(255);
+    ZP_CUDA(cudaMemcpyAsync(d_pow2.p, pow2.data(), 255 * sizeof(affine_t), cudaMemcpyHostToDevice, st));
+    DevBuf<fr_t> lo(8192), hi((npts >> 13) + 1);
+    ZP_LAUNCH(srs_power_table_kernel, dim3(32), dim3(256), 0, st, lo.p, tau, 0, 8192);
+    int nhi = (int)((npts >> 13) + 1);
+    ZP_LAUNCH(srs_power_table_kernel, dim3((nhi + 255) / 256), dim3(256), 0, st, hi.p, tau, 13, nhi);
+    srs.alloc(npts);
+    ZP_LAUNCH(srs_kernel, dim3((unsigned)((npts + 127) / 128)), dim3(128), 0, st, srs.p, npts, lo.p, hi.p, d_pow2.p);
+    ZP_CUDA(cudaStreamSynchronize(st));
+}
+
+// ---- prover key --------------------------------------------------------------------------------
+static const uint64_t* pk_coeff_ptr(const ProverKeyC& pk, int i) {
+    const uint64_t* v[PK_COUNT] = {pk.q_m_coeffs, pk.q_l_coeffs, pk.q_r_coeffs, pk.q_o_coeffs, pk.q_4_coeffs, pk.q_c_coeffs,
+                                   pk.q_hl_coeffs, pk.q_hr_coeffs, pk.q_h4_coeffs, pk.q_arith_coeffs, pk.range_selector_coeffs,
+                                   pk.logic_selector_coeffs, pk.fixed_group_add_selector_coeffs,
+                                   pk.variable_group_add_selector_coeffs, pk.q_lookup_coeffs, pk.left_sigma_coeffs,
+                                   pk.right_sigma_coeffs, pk.out_sigma_coeffs, pk.fourth_sigma_coeffs};
+    return v[i];
+}
+static const uint64_t* pk_eval_ptr(const ProverKeyC& pk, int i) {
+    const uint64_t* v[PK_COUNT] = {pk.q_m_evals, pk.q_l_evals, pk.q_r_evals, pk.q_o_evals, pk.q_4_evals, pk.q_c_evals,
+                                   pk.q_hl_evals, pk.q_hr_evals, pk.q_h4_evals, pk.q_arith_evals, pk.range_selector_evals,
+                                   pk.logic_selector_evals, pk.fixed_group_add_selector_evals,
+                                   pk.variable_group_add_selector_evals, pk.q_lookup_evals, pk.left_sigma_evals,
+                                   pk.right_sigma_evals, pk.out_sigma_evals, pk.fourth_sigma_evals};
+    return v[i];
+}
+
+void Prover::load_pk(const ProverKeyC& pk, const uint64_t* coeff_len) {
+    // reference convention when no lengths are given (gen_proof.cuh:61-62,277-278,319-329)
+    static const bool unreadable[PK_COUNT] = {true, false, false, false, false, false, false, false, false, false,
+                                              true, true, true, true, true, false, false, false, false};
+    DevBuf<fr_t> stage(n8);
+    for (int i = 0; i < PK_COUNT; i++) {
+        // evaluations (8N): upload, drop if identically zero
+        ZP_CUDA(cudaMemcpyAsync(stage.p, pk_eval_ptr(pk, i), n8 * sizeof(fr_t), cudaMemcpyHostToDevice, st));
+        bool ezero = all_zero(PS, stage.p, n8, st);
+        if (ezero) {
+            evals[i].release();
+        } else {
+            evals[i].alloc(n8);
+            ZP_CUDA(cudaMemcpyAsync(evals[i].p, stage.p, n8 * sizeof(fr_t), cudaMemcpyDeviceToDevice, st));
+        }
+        // coefficients (N)
+        size_t len = coeff_len ? (size_t)coeff_len[i] : (unreadable[i] ? 0 : n);
+        if (len > n) throw std::runtime_error("zp_prover_load_pk: coefficient array longer than N");
+        if (ezero) {
+            coeffs[i].release();
+        } else {
+            coeffs[i].alloc(n);
+            if (!coeff_len && unreadable[i]) {
+                // recover the polynomial from its coset evaluations (degree < N, so the top 7N coefficients vanish)
+                DevBuf<fr_t> full(n8);
+                ntt_run(T, NS, NTT_COSET_INV, logn + 3, evals[i].p, n8, full.p, st);
+                ZP_CUDA(cudaMemcpyAsync(coeffs[i].p, full.p, n * sizeof(fr_t), cudaMemcpyDeviceToDevice, st));
+                ZP_CUDA(cudaStreamSynchronize(st));
+            } else {
+                ZP_CUDA(cudaMemsetAsync(coeffs[i].p, 0, n * sizeof(fr_t), st));
+                if (len) ZP_CUDA(cudaMemcpyAsync(coeffs[i].p, pk_coeff_ptr(pk, i), len * sizeof(fr_t), cudaMemcpyHostToDevice, st));
+            }
+        }
+        ZP_CUDA(cudaStreamSynchronize(st));
+    }
+    const uint64_t* tb[4] = {pk.table1, pk.table2, pk.table3, pk.table4};
+    table_zero = true;
+    for (int c = 0; c < 4; c++) {
+        table[c].alloc(n);
+        ZP_CUDA(cudaMemcpyAsync(table[c].p, tb[c], n * sizeof(fr_t), cudaMemcpyHostToDevice, st));
+        if (!all_zero(PS, table[c].p, n, st)) table_zero = false;
+    }
+    finish_pk();
+}
+
+void Prover::preprocess(const uint64_t* const* selector_evals, const uint64_t* const* tables) {
+    DevBuf<fr_t> stage(n);
+    for (int i = 0; i < PK_COUNT; i++) {
+        if (!selector_evals[i]) {
+            coeffs[i].release();
+            evals[i].release();
+            continue;
+        }
+        ZP_CUDA(cudaMemcpyAsync(stage.p, selector_evals[i], n * sizeof(fr_t), cudaMemcpyHostToDevice, st));
+        if (all_zero(PS, stage.p, n, st)) {
+            coeffs[i].release();
+            evals[i].release();
+            continue;
+        }
+        coeffs[i].alloc(n);
+        evals[i].alloc(n8);
+        ntt_run(T, NS, NTT_INV, logn, stage.p, n, coeffs[i].p, st);                  // preprocess.rs:345-405
+        ntt_run(T, NS, NTT_COSET_FWD, logn + 3, coeffs[i].p, n, evals[i].p, st);    // preprocess.rs:171-246
+        ZP_CUDA(cudaStreamSynchronize(st));
+    }
+    table_zero = true;
+    for (int c = 0; c < 4; c++) {
+        table[c].alloc(n);
+        if (tables && tables[c]) {
+            ZP_CUDA(cudaMemcpyAsync(table[c].p, tables[c], n * sizeof(fr_t), cudaMemcpyHostToDevice, st));
+            if (!all_zero(PS, table[c].p, n, st)) table_zero = false;
+        } else {
+            ZP_CUDA(cudaMemsetAsync(table[c].p, 0, n * sizeof(fr_t), st));
+        }
+    }
+    finish_pk();
+}
+
+void Prover::finish_pk() {
+    for (int k = 0; k < 4; k++) {
+        if (!coeffs[PK_SIGL + k].p) throw std::runtime_error("prover key: a sigma polynomial is identically zero");
+        sigma_h[k].alloc(n);
+        ntt_run(T, NS, NTT_FWD, logn, coeffs[PK_SIGL + k].p, n, sigma_h[k].p, st);  // permutation/mod.rs:669-674
+    }
+    ZP_CUDA(cudaStreamSynchronize(st));
+    have_pk = true;
+}
+
+void Prover::commit(const fr_t* coeffs_dev, size_t ncoef, CommitmentC* out, Fq* ox, Fq* oy, bool* oinf) {
+    Scope sc(CAT_MSM);
+    if (!srs.p) throw std::runtime_error("commit: no SRS loaded");
+    Fq x, y;
+    bool inf;
+    if (!coeffs_dev || ncoef == 0) {
+        host::G1::infinity().to_affine(x, y, inf);
+    } else {
+        MsmConfig cfg = msm_config_for(ncoef);
+        msm_launch(MW, cfg, srs.p, coeffs_dev, ncoef, st);
+        host::G1 r = msm_collect(MW, cfg, st);
+        r.to_affine(x, y, inf);
+    }
+    memcpy(out->x, x.v, 48);
+    memcpy(out->y, y.v, 48);
+    if (ox) *ox = x;
+    if (oy) *oy = y;
+    if (oinf) *oinf = inf;
+}
+
+void Prover::verifier_key(uint64_t* out23) {
+    if (!have_pk) throw std::runtime_error("verifier_key: no prover key");
+    CommitmentC* o = reinterpret_cast<CommitmentC*>(out23);
+    for (int i = 0; i < PK_COUNT; i++) commit(coeffs[i].p, coeffs[i].p ? n : 0, &o[i]);
+    DevBuf<fr_t> tp(n);
+    for (int c = 0; c < 4; c++) {
+        ntt_run(T, NS, NTT_INV, logn, table[c].p, n, tp.p, st);
+        commit(tp.p, n, &o[PK_COUNT + c]);
+    }
+}
+
+// lookup/multiset.rs:131-176 on the host (general plookup tables; the Merkle circuit never gets here)
+static void combine_split_host(const std::vector<fr_t>& t, const std::vector<fr_t>& f, std::vector<fr_t>& h1, std::vector<fr_t>& h2) {
+    struct Key {
+        uint64_t v[4];
+        bool operator==(const Key& o) const { return memcmp(v, o.v, 32) == 0; }
+    };
+    struct KeyHash {
+        size_t operator()(const Key& k) const { return (size_t)(k.v[0] * 0x9e3779b97f4a7c15ULL ^ k.v[1] ^ (k.v[2] << 7) ^ (k.v[3] >> 3)); }
+    };
+    std::unordered_map<Key, size_t, KeyHash> index;
+    std::vector<fr_t> order;
+    std::vector<size_t> count;
+    auto key = [](const fr_t& x) { Key k; memcpy(k.v, x.l, 32); return k; };
+    for (const fr_t& e : t) {
+        auto it = index.find(key(e));
+        if (it == index.end()) {
+            index.emplace(key(e), order.size());
+            order.push_back(e);
+            count.push_back(1);
+        } else {
+            count[it->second]++;
+        }
+    }
+    for (const fr_t& e : f) {
+        auto it = index.find(key(e));
+        if (it == index.end()) throw std::runtime_error("lookup: query element not in table (Error::ElementNotIndexed)");
+        count[it->second]++;
+    }
+    h1.clear();
+    h2.clear();
+    int parity = 0;
+    for (size_t k = 0; k < order.size(); k++) {
+        size_t half = count[k] / 2;
+        h1.insert(h1.end(), half, order[k]);
+        h2.insert(h2.end(), half, order[k]);
+        if (count[k] & 1) {
+            if (parity) { h2.push_back(order[k]); parity = 0; }
+            else { h1.push_back(order[k]); parity = 1; }
+        }
+    }
+}
+
+static inline fr_t D(const Fr& a) { return host::to_dev(a); }
+static inline Fr H(const fr_t& a) { return host::to_host(a); }
+static void put_fr(uint64_t* dst, const Fr& a) { memcpy(dst, a.v, 32); }
+
+void Prover::prove(const CircuitC& c, ProofC* out) {
+    if (!have_pk) throw std::runtime_error("zp_prover_prove: no prover key loaded");
+    if (!srs.p) throw std::runtime_error("zp_prover_prove: no SRS loaded");
+    if (c.n > n || c.n == 0) throw std::runtime_error("zp_prover_prove: circuit size does not fit the domain");
+    PhaseTimer timer(st);
+    g_timer = &timer;
+    struct TimerGuard { ~TimerGuard() { g_timer = nullptr; } } timer_guard;
+    int total_id = timer.begin(CAT_TOTAL);
+    memset(out, 0, sizeof(ProofC));
+    const size_t cn = (size_t)c.n;
+
+    // ---- 0. witness upload + transcript start (gen_proof.cuh:11-22)
+    ensure_work_buffers(false);
+    const uint64_t* wires[4] = {c.w_l, c.w_r, c.w_o, c.w_4};
+    for (int k = 0; k < 4; k++) {
+        ZP_CUDA(cudaMemcpyAsync(w_ev[k].p, wires[k], cn * sizeof(fr_t), cudaMemcpyHostToDevice, st));
+        if (cn < n) ZP_CUDA(cudaMemsetAsync(w_ev[k].p + cn, 0, (n - cn) * sizeof(fr_t), st));
+    }
+    ZP_CUDA(cudaMemcpyAsync(qlk_ev.p, c.q_lookup, cn * sizeof(fr_t), cudaMemcpyHostToDevice, st));
+    bool lookup_on = !(table_zero && all_zero(PS, qlk_ev.p, cn, st));
+    if (lookup_on) ensure_work_buffers(true);
+
+    MerlinTranscript tr(label);
+    Fr pi_val = Fr::from_canonical(c.pi);  // CircuitC.pi is canonical (prover.rs:721-725)
+    std::vector<std::pair<uint64_t, Fr>> pis;
+    if (!pi_val.is_zero()) pis.push_back({c.intended_pi_pos, pi_val});  // PublicInputs keeps non-zero values only
+    tr.append_public_inputs("pi", pis);
+
+    // ---- 1. witness polynomials (prover.rs:192-228)
+    CommitmentC* comm = &out->a_comm;  // 19 consecutive CommitmentC
+    static const char* wl[4] = {"w_l", "w_r", "w_o", "w_4"};
+    for (int k = 0; k < 4; k++) {
+        { Scope s(CAT_NTT); ntt_run(T, NS, NTT_INV, logn, w_ev[k].p, n, w_poly[k].p, st); }
+        Fq x, y; bool inf;
+        commit(w_poly[k].p, n, &comm[k], &x, &y, &inf);
+        tr.append_point(wl[k], x, y, inf);
+    }
+
+    // ---- 2. lookup polynomials (prover.rs:230-329)
+    Fr zeta = tr.challenge_scalar("zeta");
+    tr.append_scalar("zeta", zeta);
+    {
+        Fq x, y; bool inf;
+        if (lookup_on) {
+            { Scope s(CAT_OTHER);
+              compress4(t_ev.p, table[0].p, table[1].p, table[2].p, table[3].p, D(zeta), n, st);
+              query_f(f_ev.p, w_ev[0].p, w_ev[1].p, w_ev[2].p, w_ev[3].p, qlk_ev.p, cn, t_ev.p, D(zeta), n, st); }
+            { Scope s(CAT_NTT);
+              ntt_run(T, NS, NTT_INV, logn, t_ev.p, n, table_poly.p, st);
+              ntt_run(T, NS, NTT_INV, logn, f_ev.p, n, f_poly.p, st); }
+            commit(f_poly.p, n, &comm[5], &x, &y, &inf);
+            tr.append_point("f", x, y, inf);
+            // h1, h2 = combine_split(t, f): host merge (general plookup path)
+            std::vector<fr_t> ht(n), hf(n), hh1, hh2;
+            ZP_CUDA(cudaMemcpyAsync(ht.data(), t_ev.p, n * sizeof(fr_t), cudaMemcpyDeviceToHost, st));
+            ZP_CUDA(cudaMemcpyAsync(hf.data(), f_ev.p, n * sizeof(fr_t), cudaMemcpyDeviceToHost, st));
+            ZP_CUDA(cudaStreamSynchronize(st));
+            combine_split_host(ht, hf, hh1, hh2);
+            if (hh1.size() != n || hh2.size() != n) throw std::runtime_error("lookup: combine_split produced uneven halves");
+            ZP_CUDA(cudaMemcpyAsync(h1_ev.p, hh1.data(), n * sizeof(fr_t), cudaMemcpyHostToDevice, st));
+            ZP_CUDA(cudaMemcpyAsync(h2_ev.p, hh2.data(), n * sizeof(fr_t), cudaMemcpyHostToDevice, st));
+            { Scope s(CAT_NTT);
+              ntt_run(T, NS, NTT_INV, logn, h1_ev.p, n, h1_poly.p, st);
+              ntt_run(T, NS, NTT_INV, logn, h2_ev.p, n, h2_poly.p, st); }
+            ZP_CUDA(cudaStreamSynchronize(st));  // hh1/hh2 go out of scope
+            commit(h1_poly.p, n, &comm[6], &x, &y, &inf);
+            tr.append_point("h1", x, y, inf);
+            commit(h2_poly.p, n, &comm[7], &x, &y, &inf);
+            tr.append_point("h2", x, y, inf);
+        } else {
+            // table == 0 and q_lookup == 0: t = f = h1 = h2 = 0, commitments are the identity
+            commit(nullptr, 0, &comm[5], &x, &y, &inf);
+            tr.append_point("f", x, y, inf);
+            commit(nullptr, 0, &comm[6], &x, &y, &inf);
+            tr.append_point("h1", x, y, inf);
+            commit(nullptr, 0, &comm[7], &x, &y, &inf);
+            tr.append_point("h2", x, y, inf);
+        }
+    }
+
+    // ---- 3. permutation polynomials (prover.rs:331-397)
+    Fr beta = tr.challenge_scalar("beta");
+    tr.append_scalar("beta", beta);
+    Fr gamma = tr.challenge_scalar("gamma");
+    tr.append_scalar("gamma", gamma);
+    Fr delta = tr.challenge_scalar("delta");
+    tr.append_scalar("delta", delta);
+    Fr epsilon = tr.challenge_scalar("epsilon");
+    tr.append_scalar("epsilon", epsilon);
+    if (beta == gamma || beta == delta || beta == epsilon || gamma == delta || gamma == epsilon || delta == epsilon)
+        throw std::runtime_error("challenges must be different");  // prover.rs:348-353
+    {
+        const fr_t* wp[4] = {w_ev[0].p, w_ev[1].p, w_ev[2].p, w_ev[3].p};
+        const fr_t* sp[4] = {sigma_h[0].p, sigma_h[1].p, sigma_h[2].p, sigma_h[3].p};
+        { Scope s(CAT_OTHER);
+          perm_num_den(num.p, den.p, wp, sp, D(beta), D(gamma), logn, T, st);
+          ratio_inplace(num.p, den.p, n, st);
+          exclusive_prefix_product(PS, den.p, num.p, n, st); }
+        { Scope s(CAT_NTT); ntt_run(T, NS, NTT_INV, logn, num.p, n, z_poly.p, st); }
+        Fq x, y; bool inf;
+        commit(z_poly.p, n, &comm[4], &x, &y, &inf);
+        tr.append_point("z", x, y, inf);
+    }
+    if (lookup_on) {
+        { Scope s(CAT_OTHER);
+          lookup_num_den(num.p, den.p, f_ev.p, t_ev.p, h1_ev.p, h2_ev.p, D(delta), D(epsilon), n, st);
+          ratio_inplace(num.p, den.p, n, st);
+          exclusive_prefix_product(PS, den.p, num.p, n, st); }
+        { Scope s(CAT_NTT); ntt_run(T, NS, NTT_INV, logn, num.p, n, z2_poly.p, st); }
+        commit(z2_poly.p, n, &comm[8]);
+    } else {
+        // every lookup ratio is (1+d) e * e(1+d) / (e(1+d))^2 = 1  =>  z2 = 1 on H, z2(X) = 1
+        ZP_CUDA(cudaMemsetAsync(z2_poly.p, 0, n * sizeof(fr_t), st));
+        fr_t one = fr_t::one();
+        ZP_CUDA(cudaMemcpyAsync(z2_poly.p, &one, sizeof(fr_t), cudaMemcpyHostToDevice, st));
+        ZP_CUDA(cudaStreamSynchronize(st));
+        commit(z2_poly.p, 1, &comm[8]);
+    }
+    // z_2 commitment is NOT appended to the transcript (prover.rs:395-397)
+
+    // public-input polynomial (pi.rs:103-116)
+    ZP_CUDA(cudaMemsetAsync(num.p, 0, n * sizeof(fr_t), st));
+    fr_t pi_dev = D(pi_val);
+    if (!pis.empty()) ZP_CUDA(cudaMemcpyAsync(num.p + c.intended_pi_pos, &pi_dev, sizeof(fr_t), cudaMemcpyHostToDevice, st));
+    { Scope s(CAT_NTT); ntt_run(T, NS, NTT_INV, logn, num.p, n, pi_poly.p, st); }
+
+    // ---- 4. quotient polynomial (prover.rs:402-489, quotient_poly.rs:34-206)
+    Fr alpha = tr.challenge_scalar("alpha");
+    tr.append_scalar("alpha", alpha);
+    Fr range_sep = tr.challenge_scalar("range separation challenge");
+    tr.append_scalar("range seperation challenge", range_sep);
+    Fr logic_sep = tr.challenge_scalar("logic separation challenge");
+    tr.append_scalar("logic seperation challenge", logic_sep);
+    Fr fixed_sep = tr.challenge_scalar("fixed base separation challenge");
+    tr.append_scalar("fixed base separation challenge", fixed_sep);
+    Fr var_sep = tr.challenge_scalar("variable base separation challenge");
+    tr.append_scalar("variable base separation challenge", var_sep);
+    Fr lookup_sep = tr.challenge_scalar("lookup separation challenge");
+    tr.append_scalar("lookup separation challenge", lookup_sep);
+
+    // JubJub d (ed-on-bls12-381), Montgomery literal — lib/PLONK/src/bls12_381/edwards.cu:20-31
+    static const uint64_t JUBJUB_D[4] = {3049539848285517488ULL, 18189135023605205683ULL, 8793554888777148625ULL,
+                                         6339087681201251886ULL};
+    Fr coeff_d;
+    memcpy(coeff_d.v, JUBJUB_D, 32);
+    {
+        { Scope s(CAT_NTT);
+          for (int k = 0; k < 4; k++) ntt_run(T, NS, NTT_COSET_FWD, logn + 3, w_poly[k].p, n, w8[k].p, st);
+          ntt_run(T, NS, NTT_COSET_FWD, logn + 3, z_poly.p, n, z8.p, st);
+          ntt_run(T, NS, NTT_COSET_FWD, logn + 3, pi_poly.p, n, pi8.p, st);
+          if (lookup_on) {
+              ntt_run(T, NS, NTT_COSET_FWD, logn + 3, z2_poly.p, n, z28.p, st);
+              ntt_run(T, NS, NTT_COSET_FWD, logn + 3, f_poly.p, n, f8.p, st);
+              ntt_run(T, NS, NTT_COSET_FWD, logn + 3, table_poly.p, n, tb8.p, st);
+              ntt_run(T, NS, NTT_COSET_FWD, logn + 3, h1_poly.p, n, h18.p, st);
+              ntt_run(T, NS, NTT_COSET_FWD, logn + 3, h2_poly.p, n, h28.p, st);
+          } }
+        QuotientArgs qa;
+        qa.logn = logn;
+        for (int k = 0; k < 4; k++) qa.w[k] = w8[k].p;
+        qa.z = z8.p;
+        qa.z2 = lookup_on ? z28.p : nullptr;
+        qa.f = f8.p; qa.table = tb8.p; qa.h1 = h18.p; qa.h2 = h28.p;
+        qa.pi = pi8.p;
+        qa.l1 = l1_coset.p;
+        for (int i = 0; i < 15; i++) qa.sel[i] = evals[i].p;
+        for (int k = 0; k < 4; k++) qa.sigma[k] = evals[PK_SIGL + k].p;
+        qa.alpha = D(alpha); qa.beta = D(beta); qa.gamma = D(gamma); qa.delta = D(delta); qa.epsilon = D(epsilon);
+        qa.zeta = D(zeta); qa.range_sep = D(range_sep); qa.logic_sep = D(logic_sep); qa.fixed_sep = D(fixed_sep);
+        qa.var_sep = D(var_sep); qa.lookup_sep = D(lookup_sep);
+        // Z_H on the coset: g^N * w8^k - 1 (preprocess.rs:498-520), inverted once per residue
+        Fr g = H(fr_generator_host());
+        Fr gn = g.pow_u64(n), w8 = H(T.omega[3]), p = gn;
+        for (int k = 0; k < 8; k++) {
+            qa.vh_inv[k] = D((p - Fr::one()).inverse());
+            p = p * w8;
+        }
+        qa.coeff_d = D(coeff_d);
+        qa.w_lo = T.w_lo.p;
+        qa.w_hi = T.w_hi.p;
+        qa.g = fr_generator_host();
+        qa.out = quot.p;
+        { Scope s(CAT_QUOT); quotient_evals(qa, st); }
+        { Scope s(CAT_NTT); ntt_run(T, NS, NTT_COSET_INV, logn + 3, quot.p, n8, t_poly.p, st); }
+    }
+    static const char* tl[8] = {"t_1", "t_2", "t_3", "t_4", "t_5", "t_6", "t_7", "t_8"};
+    bool t_zero[8];
+    for (int k = 0; k < 8; k++) {
+        Fq x, y; bool inf;
+        t_zero[k] = all_zero(PS, t_poly.p + (size_t)k * n, n, st);
+        if (t_zero[k]) commit(nullptr, 0, &comm[9 + k], &x, &y, &inf);
+        else commit(t_poly.p + (size_t)k * n, n, &comm[9 + k], &x, &y, &inf);
+        tr.append_point(tl[k], x, y, inf);
+    }
+
+    // ---- 5. linearisation (prover.rs:491-572, linearisation_poly.rs:164-372)
+    Fr z_ch = tr.challenge_scalar("z");
+    tr.append_scalar("z", z_ch);
+    Fr omega = H(T.omega[logn]);
+    Fr zs = z_ch * omega;
+    // evaluation plan: (slot in ProofEvaluationsC, polynomial, point)
+    enum { E_A = 0, E_B, E_C, E_D, E_LSIG, E_RSIG, E_OSIG, E_PERM, E_QLOOKUP, E_Z2NEXT, E_H1, E_H1NEXT, E_H2, E_F, E_TABLE,
+           E_TABLENEXT, E_QARITH, E_QC, E_QL, E_QR, E_QHL, E_QHR, E_QH4, E_ANEXT, E_BNEXT, E_DNEXT, NUM_E };
+    Fr ev[NUM_E];
+    for (int i = 0; i < NUM_E; i++) ev[i] = Fr::zero();
+    {
+        struct Plan { int slot; const fr_t* poly; bool shifted; };
+        std::vector<Plan> plan = {
+            {E_A, w_poly[0].p, false}, {E_B, w_poly[1].p, false}, {E_C, w_poly[2].p, false}, {E_D, w_poly[3].p, false},
+            {E_LSIG, coeffs[PK_SIGL].p, false}, {E_RSIG, coeffs[PK_SIGR].p, false}, {E_OSIG, coeffs[PK_SIGO].p, false},
+            {E_PERM, z_poly.p, true}, {E_QARITH, coeffs[PK_QARITH].p, false}, {E_QLOOKUP, coeffs[PK_QLOOKUP].p, false},
+            {E_QC, coeffs[PK_QC].p, false}, {E_QL, coeffs[PK_QL].p, false}, {E_QR, coeffs[PK_QR].p, false},
+            {E_ANEXT, w_poly[0].p, true}, {E_BNEXT, w_poly[1].p, true}, {E_DNEXT, w_poly[3].p, true},
+            {E_QHL, coeffs[PK_QHL].p, false}, {E_QHR, coeffs[PK_QHR].p, false}, {E_QH4, coeffs[PK_QH4].p, false}};
+        if (lookup_on) {
+            plan.push_back({E_Z2NEXT, z2_poly.p, true});
+            plan.push_back({E_H1, h1_poly.p, false});
+            plan.push_back({E_H1NEXT, h1_poly.p, true});
+            plan.push_back({E_H2, h2_poly.p, false});
+            plan.push_back({E_F, f_poly.p, false});
+            plan.push_back({E_TABLE, table_poly.p, false});
+            plan.push_back({E_TABLENEXT, table_poly.p, true});
+        } else {
+            ev[E_Z2NEXT] = Fr::one();  // z2(X) = 1
+        }
+        const fr_t* polys[32];
+        fr_t points[32], results[32];
+        int slots[32], cnt = 0;
+        for (auto& pl : plan) {
+            if (!pl.poly) continue;  // identically-zero polynomial evaluates to 0
+            polys[cnt] = pl.poly;
+            points[cnt] = D(pl.shifted ? zs : z_ch);
+            slots[cnt] = pl.slot;
+            cnt++;
+        }
+        { Scope s(CAT_OTHER); evaluate_many(PS, polys, points, cnt, n, results, st); }
+        for (int i = 0; i < cnt; i++) ev[slots[i]] = H(results[i]);
+    }
+    Fr vanishing = z_ch.pow_u64(n) - Fr::one();
+    Fr z_to_n = vanishing + Fr::one();
+    Fr l1_eval = vanishing * (Fr::from_u64(n) * (z_ch - Fr::one())).inverse();  // proof.rs:647-658
+    {
+        GateVals<Fr> g;
+        g.a = ev[E_A]; g.b = ev[E_B]; g.c = ev[E_C]; g.d = ev[E_D];
+        g.a_next = ev[E_ANEXT]; g.b_next = ev[E_BNEXT]; g.d_next = ev[E_DNEXT];
+        g.q_l = ev[E_QL]; g.q_r = ev[E_QR]; g.q_c = ev[E_QC];
+        std::vector<const fr_t*> lp;
+        std::vector<fr_t> ls;
+        auto term = [&](const fr_t* poly, const Fr& s) {
+            if (!poly) return;
+            lp.push_back(poly);
+            ls.push_back(D(s));
+        };
+        auto pow5 = [](const Fr& x) { Fr s = x.sqr(); return s.sqr() * x; };
+        Fr qa = ev[E_QARITH];
+        term(coeffs[PK_QM].p, g.a * g.b * qa);          // arithmetic.rs:83-101
+        term(coeffs[PK_QL].p, g.a * qa);
+        term(coeffs[PK_QR].p, g.b * qa);
+        term(coeffs[PK_QO].p, g.c * qa);
+        term(coeffs[PK_Q4].p, g.d * qa);
+        term(coeffs[PK_QHL].p, pow5(g.a) * qa);
+        term(coeffs[PK_QHR].p, pow5(g.b) * qa);
+        term(coeffs[PK_QH4].p, pow5(g.d) * qa);
+        term(coeffs[PK_QC].p, qa);
+        if (coeffs[PK_RANGE].p) term(coeffs[PK_RANGE].p, range_constraints(range_sep, g));
+        if (coeffs[PK_LOGIC].p) term(coeffs[PK_LOGIC].p, logic_constraints(logic_sep, g));
+        if (coeffs[PK_FIXED].p) term(coeffs[PK_FIXED].p, fbsm_constraints(fixed_sep, g, coeff_d));
+        if (coeffs[PK_VAR].p) term(coeffs[PK_VAR].p, curve_add_constraints(var_sep, g, coeff_d));
+        // lookup.rs:155-215
+        Fr lsep_sq = lookup_sep.sqr(), lsep_cu = lookup_sep * lsep_sq;
+        Fr opd = delta + Fr::one(), eopd = epsilon * opd;
+        term(coeffs[PK_QLOOKUP].p, (lc4(g.a, g.b, g.c, g.d, zeta) - ev[E_F]) * lookup_sep);
+        {
+            Fr b0 = epsilon + ev[E_F];
+            Fr b1 = eopd + ev[E_TABLE] + delta * ev[E_TABLENEXT];
+            Fr b2 = l1_eval * lsep_cu;
+            term(z2_poly.p, opd * b0 * b1 * lsep_sq + b2);
+            Fr c0 = (Fr::zero() - ev[E_Z2NEXT]) * lsep_sq;
+            Fr c1 = eopd + ev[E_H2] + delta * ev[E_H1NEXT];
+            if (lookup_on) term(h1_poly.p, c0 * c1);
+        }
+        // permutation.rs:156-296
+        {
+            Fr beta_z = beta * z_ch;
+            Fr k1 = Fr::from_u64(7), k2 = Fr::from_u64(13), k3 = Fr::from_u64(17);
+            Fr a0 = g.a + beta_z + gamma;
+            Fr a1 = g.b + k1 * beta_z + gamma;
+            Fr a2 = g.c + k2 * beta_z + gamma;
+            Fr a3 = g.d + k3 * beta_z + gamma;
+            term(z_poly.p, a0 * a1 * a2 * a3 * alpha);
+            Fr b0 = g.a + beta * ev[E_LSIG] + gamma;
+            Fr b1 = g.b + beta * ev[E_RSIG] + gamma;
+            Fr b2 = g.c + beta * ev[E_OSIG] + gamma;
+            Fr b = b0 * b1 * b2 * (beta * ev[E_PERM]) * alpha;
+            term(coeffs[PK_SIG4].p, Fr::zero() - b);
+            term(z_poly.p, l1_eval * alpha.sqr());
+        }
+        // - Z_H(z) * sum_k z^{kN} t_{k+1}(X)
+        Fr zp = Fr::one();
+        for (int k = 0; k < 8; k++) {
+            if (!t_zero[k]) term(t_poly.p + (size_t)k * n, Fr::zero() - (zp * vanishing));
+            zp = zp * z_to_n;
+        }
+        { Scope s(CAT_OTHER); lincomb(lin.p, lp.data(), ls.data(), (int)lp.size(), n, st); }
+    }
+    // evaluations into the transcript (prover.rs:532-572) and the proof
+    static const char* en[NUM_E] = {"a_eval", "b_eval", "c_eval", "d_eval", "left_sig_eval", "right_sig_eval", "out_sig_eval",
+                                    "perm_eval", "q_lookup_eval", "lookup_perm_eval", "h_1_eval", "h_1_next_eval", "h_2_eval",
+                                    "f_eval", "", "", "q_arith_eval", "q_c_eval", "q_l_eval", "q_r_eval", "q_hl_eval", "q_hr_eval",
+                                    "q_h4_eval", "a_next_eval", "b_next_eval", "d_next_eval"};
+    static const int order[] = {E_A, E_B, E_C, E_D, E_LSIG, E_RSIG, E_OSIG, E_PERM, E_F, E_QLOOKUP, E_Z2NEXT, E_H1, E_H1NEXT, E_H2,
+                                E_QARITH, E_QC, E_QL, E_QR, E_QHL, E_QHR, E_QH4, E_ANEXT, E_BNEXT, E_DNEXT};
+    for (int idx : order) tr.append_scalar(en[idx], ev[idx]);
+    uint64_t* eout = reinterpret_cast<uint64_t*>(&out->evaluations);
+    for (int i = 0; i < NUM_E; i++) put_fr(eout + 4 * i, ev[i]);
+
+    // ---- 6. openings (prover.rs:574-636; kzg10.cu:87-146)
+    auto open = [&](const std::vector<const fr_t*>& polys, const Fr& point, const Fr& chal, CommitmentC* dst) {
+        std::vector<const fr_t*> lp;
+        std::vector<fr_t> ls;
+        Fr cj = Fr::one();
+        for (const fr_t* p : polys) {
+            if (p) {
+                lp.push_back(p);
+                ls.push_back(D(cj));
+            }
+            cj = cj * chal;
+        }
+        { Scope s(CAT_OTHER);
+          lincomb(comb.p, lp.data(), ls.data(), (int)lp.size(), n, st);
+          divide_by_linear(PS, comb.p, n, D(point), wit.p, st); }
+        commit(wit.p, n, dst);
+    };
+    Fr aw = tr.challenge_scalar("aggregate_witness");
+    open({lin.p, coeffs[PK_SIGL].p, coeffs[PK_SIGR].p, coeffs[PK_SIGO].p, lookup_on ? f_poly.p : nullptr,
+          lookup_on ? h2_poly.p : nullptr, lookup_on ? table_poly.p : nullptr, w_poly[0].p, w_poly[1].p, w_poly[2].p, w_poly[3].p},
+         z_ch, aw, &out->aw_opening);
+    Fr saw = tr.challenge_scalar("aggregate_witness");
+    open({z_poly.p, w_poly[0].p, w_poly[1].p, w_poly[3].p, lookup_on ? h1_poly.p : nullptr, z2_poly.p,
+          lookup_on ? table_poly.p : nullptr},
+         zs, saw, &out->saw_opening);
+
+    timer.end(total_id);
+    timer.collect(last_ms);
+    last_ms[CAT_OTHER] = last_ms[CAT_TOTAL] - last_ms[CAT_NTT] - last_ms[CAT_MSM] - last_ms[CAT_QUOT];
+}
+
+}  // namespace zp

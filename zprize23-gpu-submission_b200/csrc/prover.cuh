@@ -1,0 +1,66 @@
+// Resident prover context and the gen_proof protocol driver (interface of prover.cu).
+#pragma once
+#include "../../include/zprize_b200.h"
+#include "common.cuh"
+#include "ntt.cuh"
+#include "msm.cuh"
+#include "poly.cuh"
+#include "transcript.hpp"
+#include <string>
+
+namespace zp {
+
+// ProverKeyC polynomial order: q_m,q_l,q_r,q_o,q_4,q_c,q_hl,q_hr,q_h4,q_arith,range,logic,fixed,variable,
+// q_lookup, left/right/out/fourth sigma
+enum PkPoly {
+    PK_QM = 0, PK_QL, PK_QR, PK_QO, PK_Q4, PK_QC, PK_QHL, PK_QHR, PK_QH4, PK_QARITH, PK_RANGE, PK_LOGIC, PK_FIXED, PK_VAR,
+    PK_QLOOKUP, PK_SIGL, PK_SIGR, PK_SIGO, PK_SIG4, PK_COUNT
+};
+
+struct PhaseTimer;
+
+struct Prover {
+    int logn;
+    size_t n, n8;
+    cudaStream_t st = 0;
+    std::string label = "Merkle tree";
+    NttTables T;
+    NttScratch NS;
+    PolyScratch PS;
+    MsmWorkspace MW;
+
+    // ---- resident inputs (uploaded / built once, reused by every proof)
+    DevBuf<affine_t> srs;
+    DevBuf<fr_t> coeffs[PK_COUNT];   // N each; empty = identically zero
+    DevBuf<fr_t> evals[PK_COUNT];    // 8N each; empty = identically zero
+    DevBuf<fr_t> sigma_h[4];         // sigma evaluations on H
+    DevBuf<fr_t> table[4];           // padded lookup columns on H
+    bool table_zero = true;          // all four columns identically zero
+    DevBuf<fr_t> l1_coset;           // L_1 on g*H_8N
+    bool have_pk = false;
+
+    // ---- per-proof work buffers (allocated once)
+    DevBuf<fr_t> w_ev[4], w_poly[4], w8[4];
+    DevBuf<fr_t> qlk_ev;
+    DevBuf<fr_t> z_poly, z8, z2_poly, z28;
+    DevBuf<fr_t> t_ev, f_ev, h1_ev, h2_ev, table_poly, f_poly, h1_poly, h2_poly, tb8, f8, h18, h28;
+    DevBuf<fr_t> pi_poly, pi8, quot, t_poly;
+    DevBuf<fr_t> num, den, lin, comb, wit;
+    double last_ms[5] = {0, 0, 0, 0, 0};
+
+    explicit Prover(int logn_);
+    ~Prover();
+    void ensure_work_buffers(bool lookup);
+    void load_srs(const uint64_t* pts, size_t npts);
+    void generate_srs(const fr_t& tau, size_t npts);
+    void load_pk(const ProverKeyC& pk, const uint64_t* coeff_len);
+    void preprocess(const uint64_t* const* selector_evals, const uint64_t* const* tables);
+    void finish_pk();
+    void verifier_key(uint64_t* out23);
+    void prove(const CircuitC& c, ProofC* out);
+
+    // commit to n coefficients (Montgomery) on the device; returns affine point (host)
+    void commit(const fr_t* coeffs_dev, size_t ncoef, CommitmentC* out, host::Fq* ox = nullptr, host::Fq* oy = nullptr, bool* oinf = nullptr);
+};
+
+}  // namespace zp

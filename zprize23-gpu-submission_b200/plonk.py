@@ -1,0 +1,337 @@
+"""Host-side mirror of the reference's FFI surface for the PLONK prover hot path.
+
+The reference's host side is Rust (`Prover::prove_pnp`, "Prize 1B/plonk-core/src/proof_system/prover.rs":693-907,
+binding `extern "C" gen_proof` declared at "Prize 1B/plonk-core/src/lib.rs":237-239).  No Rust toolchain exists in
+this image, so the marshalling layer above the C-ABI is mirrored here with ctypes: the same `#[repr(C)]` structs
+(lib.rs:53-235), the same `gen_proof(CircuitC, ProverKeyC, CommitKeyC) -> ProofC` call, plus the resident-context
+extension of include/zprize_b200.h.  All numerical work happens in libzprize_b200.so (hand-written sm_100a CUDA);
+there is no CPU path: loading fails loudly if the library is missing, and context creation fails without a GPU.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libzprize_b200.so")
+
+u64p = ctypes.POINTER(ctypes.c_uint64)
+
+
+class CommitmentC(ctypes.Structure):  # lib.rs:231-235
+    _fields_ = [("x", ctypes.c_uint64 * 6), ("y", ctypes.c_uint64 * 6)]
+
+
+def _fr_fields(names):
+    return [(n, ctypes.c_uint64 * 4) for n in names]
+
+
+class WireEvaluationsC(ctypes.Structure):  # lib.rs:53-59
+    _fields_ = _fr_fields(["a_eval", "b_eval", "c_eval", "d_eval"])
+
+
+class PermutationEvaluationsC(ctypes.Structure):  # lib.rs:61-67
+    _fields_ = _fr_fields(["left_sigma_eval", "right_sigma_eval", "out_sigma_eval", "permutation_eval"])
+
+
+class LookupEvaluationsC(ctypes.Structure):  # lib.rs:100-110
+    _fields_ = _fr_fields(["q_lookup_eval", "z2_next_eval", "h1_eval", "h1_next_eval", "h2_eval", "f_eval", "table_eval",
+                           "table_next_eval"])
+
+
+class CustomEvaluationsC(ctypes.Structure):  # lib.rs:69-81
+    _fields_ = _fr_fields(["q_arith_eval", "q_c_eval", "q_l_eval", "q_r_eval", "q_hl_eval", "q_hr_eval", "q_h4_eval",
+                           "a_next_eval", "b_next_eval", "d_next_eval"])
+
+
+class ProofEvaluationsC(ctypes.Structure):  # lib.rs:111-118
+    _fields_ = [("wire_evals", WireEvaluationsC), ("perm_evals", PermutationEvaluationsC),
+                ("lookup_evals", LookupEvaluationsC), ("custom_evals", CustomEvaluationsC)]
+
+
+COMMITMENT_NAMES = ["a_comm", "b_comm", "c_comm", "d_comm", "z_comm", "f_comm", "h_1_comm", "h_2_comm", "z_2_comm",
+                    "t_1_comm", "t_2_comm", "t_3_comm", "t_4_comm", "t_5_comm", "t_6_comm", "t_7_comm", "t_8_comm",
+                    "aw_opening", "saw_opening"]
+EVALUATION_NAMES = (["a_eval", "b_eval", "c_eval", "d_eval", "left_sigma_eval", "right_sigma_eval", "out_sigma_eval",
+                     "permutation_eval", "q_lookup_eval", "z2_next_eval", "h1_eval", "h1_next_eval", "h2_eval", "f_eval",
+                     "table_eval", "table_next_eval", "q_arith_eval", "q_c_eval", "q_l_eval", "q_r_eval", "q_hl_eval",
+                     "q_hr_eval", "q_h4_eval", "a_next_eval", "b_next_eval", "d_next_eval"])
+
+
+class ProofC(ctypes.Structure):  # lib.rs:120-142
+    _fields_ = [(n, CommitmentC) for n in COMMITMENT_NAMES] + [("evaluations", ProofEvaluationsC)]
+
+    def to_words(self):
+        """The 2656-byte image as 332 little-endian u64 words."""
+        return np.frombuffer(bytes(self), dtype=np.uint64).copy()
+
+
+class CircuitC(ctypes.Structure):  # lib.rs:144-155
+    _fields_ = [("n", ctypes.c_uint64), ("lookup_len", ctypes.c_uint64), ("intended_pi_pos", ctypes.c_uint64),
+                ("q_lookup", u64p), ("pi", u64p), ("w_l", u64p), ("w_r", u64p), ("w_o", u64p), ("w_4", u64p)]
+
+
+PK_POLY_NAMES = ["q_m", "q_l", "q_r", "q_o", "q_4", "q_c", "q_hl", "q_hr", "q_h4", "q_arith", "range_selector",
+                 "logic_selector", "fixed_group_add_selector", "variable_group_add_selector", "q_lookup"]
+PK_SIGMA_NAMES = ["left_sigma", "right_sigma", "out_sigma", "fourth_sigma"]
+
+
+def _pk_fields():
+    f = []
+    for n in PK_POLY_NAMES:
+        f += [(n + "_coeffs", u64p), (n + "_evals", u64p)]
+    f += [("table1", u64p), ("table2", u64p), ("table3", u64p), ("table4", u64p)]
+    for n in PK_SIGMA_NAMES:
+        f += [(n + "_coeffs", u64p), (n + "_evals", u64p)]
+    f += [("linear_evaluations", u64p), ("v_h_coset_8n", u64p)]
+    return f
+
+
+class ProverKeyC(ctypes.Structure):  # lib.rs:157-223
+    _fields_ = _pk_fields()
+
+
+class CommitKeyC(ctypes.Structure):  # lib.rs:225-229
+    _fields_ = [("powers_of_g", u64p), ("powers_of_gamma_g", u64p)]
+
+
+assert ctypes.sizeof(ProofC) == 2656 and ctypes.sizeof(ProverKeyC) == 44 * 8 and ctypes.sizeof(CircuitC) == 72
+
+
+class ZprizeError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library(path=None):
+    """Loads libzprize_b200.so (built in-tree by build.py).  No fallback: a missing library is an error."""
+    global _lib
+    path = path or LIB_PATH
+    if _lib is not None and getattr(_lib, "_zp_path", None) == path:
+        return _lib
+    if not os.path.exists(path):
+        raise ZprizeError("%s not found: build it with `python %s` (nvcc, sm_100a); there is no CPU fallback"
+                          % (path, os.path.join(_HERE, "build.py")))
+    lib = ctypes.CDLL(path)
+    lib._zp_path = path
+    vp, ci, cs, cd = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_double
+    dp = ctypes.POINTER(ctypes.c_double)
+    sig = {
+        "zp_last_error": (ctypes.c_char_p, []),
+        "zp_launch_count": (ctypes.c_uint64, []),
+        "zp_device_available": (ci, []),
+        "zp_prover_create": (vp, [ci]),
+        "zp_prover_destroy": (None, [vp]),
+        "zp_prover_set_label": (ci, [vp, ctypes.c_char_p]),
+        "zp_prover_load_srs": (ci, [vp, u64p, cs]),
+        "zp_prover_generate_srs": (ci, [vp, u64p, cs]),
+        "zp_prover_read_srs": (ci, [vp, u64p, cs]),
+        "zp_prover_load_pk": (ci, [vp, ctypes.POINTER(ProverKeyC), u64p]),
+        "zp_prover_preprocess": (ci, [vp, ctypes.POINTER(u64p), ctypes.POINTER(u64p)]),
+        "zp_prover_verifier_key": (ci, [vp, u64p]),
+        "zp_prover_prove": (ci, [vp, ctypes.POINTER(CircuitC), ctypes.POINTER(ProofC)]),
+        "zp_prover_last_timing": (ci, [vp, dp, ci]),
+        "zp_ntt_host": (ci, [vp, ci, ci, u64p, u64p]),
+        "zp_msm_host": (ci, [vp, u64p, cs, u64p]),
+        "zp_msm_points_host": (ci, [vp, u64p, u64p, cs, ci, u64p]),
+        "zp_poly_eval_host": (ci, [vp, u64p, cs, u64p, u64p]),
+        "zp_poly_divide_host": (ci, [vp, u64p, cs, u64p, u64p]),
+        "zp_prefix_product_host": (ci, [vp, u64p, cs, u64p]),
+        "zp_bench_alloc": (ci, [vp, ci, cs]),
+        "zp_bench_upload": (ci, [vp, ci, u64p, cs]),
+        "zp_bench_download": (ci, [vp, ci, u64p, cs]),
+        "zp_bench_ntt": (ci, [vp, ci, ci, ci, ci, ci, dp]),
+        "zp_bench_msm": (ci, [vp, ci, cs, ci, dp, u64p]),
+        "zp_bench_msm_breakdown": (ci, [vp, dp]),
+        "zp_bench_int_pipe": (ci, [vp, ci, dp]),
+        "gen_proof": (ProofC, [CircuitC, ProverKeyC, CommitKeyC]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+EXPORTED_SYMBOLS = ["gen_proof", "zp_last_error", "zp_launch_count", "zp_device_available", "zp_prover_create",
+                    "zp_prover_destroy", "zp_prover_set_label", "zp_prover_load_srs", "zp_prover_generate_srs",
+                    "zp_prover_read_srs", "zp_prover_load_pk", "zp_prover_preprocess", "zp_prover_verifier_key",
+                    "zp_prover_prove", "zp_prover_last_timing", "zp_ntt_host", "zp_msm_host", "zp_msm_points_host",
+                    "zp_poly_eval_host", "zp_poly_divide_host", "zp_prefix_product_host", "zp_bench_alloc",
+                    "zp_bench_upload", "zp_bench_download", "zp_bench_ntt", "zp_bench_msm", "zp_bench_msm_breakdown",
+                    "zp_bench_int_pipe"]
+
+
+def as_u64p(a):
+    """Pointer to a C-contiguous uint64 numpy array (kept alive by the caller)."""
+    if a is None:
+        return ctypes.cast(None, u64p)
+    assert a.dtype == np.uint64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(u64p)
+
+
+def make_circuit(n, lookup_len, pi_pos, q_lookup, pi_canonical, w_l, w_r, w_o, w_4):
+    """CircuitC over numpy uint64 arrays ([n,4] Fr words each; pi: 4 words, canonical form)."""
+    c = CircuitC()
+    c.n, c.lookup_len, c.intended_pi_pos = n, lookup_len, pi_pos
+    c.q_lookup, c.pi = as_u64p(q_lookup), as_u64p(pi_canonical)
+    c.w_l, c.w_r, c.w_o, c.w_4 = as_u64p(w_l), as_u64p(w_r), as_u64p(w_o), as_u64p(w_4)
+    c._keep = (q_lookup, pi_canonical, w_l, w_r, w_o, w_4)
+    return c
+
+
+def make_prover_key(coeffs, evals, tables, linear_evaluations=None, v_h_coset_8n=None):
+    """ProverKeyC from dicts name -> array (names of PK_POLY_NAMES + PK_SIGMA_NAMES) and 4 table columns."""
+    pk = ProverKeyC()
+    keep = []
+    for nme in PK_POLY_NAMES + PK_SIGMA_NAMES:
+        setattr(pk, nme + "_coeffs", as_u64p(coeffs.get(nme)))
+        setattr(pk, nme + "_evals", as_u64p(evals.get(nme)))
+        keep += [coeffs.get(nme), evals.get(nme)]
+    for i in range(4):
+        setattr(pk, "table%d" % (i + 1), as_u64p(tables[i]))
+    pk.linear_evaluations = as_u64p(linear_evaluations)
+    pk.v_h_coset_8n = as_u64p(v_h_coset_8n)
+    pk._keep = (keep, tables, linear_evaluations, v_h_coset_8n)
+    return pk
+
+
+def gen_proof(circuit, pk, ck, lib=None):
+    """The reference's FFI call itself: `gen_proof(CircuitC, ProverKeyC, CommitKeyC) -> ProofC` (by value)."""
+    lib = lib or load_library()
+    return lib.gen_proof(circuit, pk, ck)
+
+
+class ProverContext:
+    """Resident prover (extension of the FFI): SRS, prover key, twiddles and work buffers stay in HBM."""
+
+    def __init__(self, log_n, lib=None):
+        self.lib = lib or load_library()
+        self.log_n = log_n
+        self.n = 1 << log_n
+        self.h = self.lib.zp_prover_create(log_n)
+        if not self.h:
+            raise ZprizeError(self.lib.zp_last_error().decode())
+
+    def close(self):
+        if self.h:
+            self.lib.zp_prover_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise ZprizeError(self.lib.zp_last_error().decode())
+
+    def set_label(self, label):
+        self._ck(self.lib.zp_prover_set_label(self.h, label))
+
+    def load_srs(self, points):
+        self._ck(self.lib.zp_prover_load_srs(self.h, as_u64p(points), points.size // 12))
+
+    def generate_srs(self, tau_words, n_points=None):
+        self._ck(self.lib.zp_prover_generate_srs(self.h, as_u64p(tau_words), n_points or self.n))
+
+    def read_srs(self, n_points=None):
+        n_points = n_points or self.n
+        out = np.zeros((n_points, 12), dtype=np.uint64)
+        self._ck(self.lib.zp_prover_read_srs(self.h, as_u64p(out), n_points))
+        return out
+
+    def load_pk(self, pk, coeff_len=None):
+        cl = None if coeff_len is None else np.asarray(coeff_len, dtype=np.uint64)
+        self._ck(self.lib.zp_prover_load_pk(self.h, ctypes.byref(pk), as_u64p(cl)))
+
+    def preprocess(self, selector_evals, tables=None):
+        """selector_evals: 19 arrays (15 selectors + 4 sigmas) of N Fr on H, or None for all-zero."""
+        arr = (u64p * 19)(*[as_u64p(a) for a in selector_evals])
+        tb = None
+        if tables is not None:
+            tb = (u64p * 4)(*[as_u64p(a) for a in tables])
+        self._ck(self.lib.zp_prover_preprocess(self.h, arr, tb))
+
+    def verifier_key(self):
+        out = np.zeros((23, 12), dtype=np.uint64)
+        self._ck(self.lib.zp_prover_verifier_key(self.h, as_u64p(out)))
+        return out
+
+    def prove(self, circuit):
+        proof = ProofC()
+        self._ck(self.lib.zp_prover_prove(self.h, ctypes.byref(circuit), ctypes.byref(proof)))
+        return proof
+
+    def last_timing(self):
+        out = (ctypes.c_double * 5)()
+        self._ck(self.lib.zp_prover_last_timing(self.h, out, 5))
+        return dict(zip(["total_ms", "ntt_ms", "msm_ms", "quotient_ms", "other_ms"], list(out)))
+
+    # ---- operator entry points (function.cuh:45-113 equivalents) ----
+    def ntt(self, kind, data):
+        log_n = int(np.log2(data.shape[0]))
+        out = np.zeros_like(data)
+        self._ck(self.lib.zp_ntt_host(self.h, kind, log_n, as_u64p(data), as_u64p(out)))
+        return out
+
+    def msm(self, scalars):
+        out = np.zeros(12, dtype=np.uint64)
+        self._ck(self.lib.zp_msm_host(self.h, as_u64p(scalars), scalars.shape[0], as_u64p(out)))
+        return out
+
+    def msm_points(self, points, scalars, window_bits=0):
+        out = np.zeros(12, dtype=np.uint64)
+        self._ck(self.lib.zp_msm_points_host(self.h, as_u64p(points), as_u64p(scalars), scalars.shape[0], window_bits,
+                                             as_u64p(out)))
+        return out
+
+    def poly_eval(self, coeffs, point):
+        out = np.zeros(4, dtype=np.uint64)
+        self._ck(self.lib.zp_poly_eval_host(self.h, as_u64p(coeffs), coeffs.shape[0], as_u64p(point), as_u64p(out)))
+        return out
+
+    def poly_divide(self, coeffs, point):
+        out = np.zeros((coeffs.shape[0] - 1, 4), dtype=np.uint64)
+        self._ck(self.lib.zp_poly_divide_host(self.h, as_u64p(coeffs), coeffs.shape[0], as_u64p(point), as_u64p(out)))
+        return out
+
+    def prefix_product(self, data):
+        out = np.zeros_like(data)
+        self._ck(self.lib.zp_prefix_product_host(self.h, as_u64p(data), data.shape[0], as_u64p(out)))
+        return out
+
+    # ---- device-resident benchmark helpers ----
+    def bench_alloc(self, slot, n_fr):
+        self._ck(self.lib.zp_bench_alloc(self.h, slot, n_fr))
+
+    def bench_upload(self, slot, data):
+        self._ck(self.lib.zp_bench_upload(self.h, slot, as_u64p(data), data.size // 4))
+
+    def bench_download(self, slot, n_fr):
+        out = np.zeros((n_fr, 4), dtype=np.uint64)
+        self._ck(self.lib.zp_bench_download(self.h, slot, as_u64p(out), n_fr))
+        return out
+
+    def bench_ntt(self, kind, log_n, slot_in, slot_out, iters):
+        ms = ctypes.c_double()
+        self._ck(self.lib.zp_bench_ntt(self.h, kind, log_n, slot_in, slot_out, iters, ctypes.byref(ms)))
+        return ms.value
+
+    def bench_msm(self, slot, n, iters):
+        ms = ctypes.c_double()
+        out = np.zeros(12, dtype=np.uint64)
+        self._ck(self.lib.zp_bench_msm(self.h, slot, n, iters, ctypes.byref(ms), as_u64p(out)))
+        bd = (ctypes.c_double * 5)()
+        self._ck(self.lib.zp_bench_msm_breakdown(self.h, bd))
+        return ms.value, out, dict(zip(["digits", "scan", "scatter", "accumulate", "reduce"], list(bd)))
+
+    def bench_int_pipe(self, mode):
+        g = ctypes.c_double()
+        self._ck(self.lib.zp_bench_int_pipe(self.h, mode, ctypes.byref(g)))
+        return g.value
