@@ -78,11 +78,21 @@ struct Composer {
         }
         push_gate(r1, r2, zero_var, zero_var);
     }
+    // division by -q_o: the Poseidon gadget always uses q_o = -1, so cache the last inverse
+    Fr inv_last_in = Fr::zero(), inv_last_out = Fr::zero();
+    Fr inv_cached(const Fr& x) {
+        if (x == Fr::one()) return x;
+        if (!(x == inv_last_in)) {
+            inv_last_in = x;
+            inv_last_out = x.inverse();
+        }
+        return inv_last_out;
+    }
     // hash.rs:23-67
     uint32_t full_affine_transform_gate(const uint32_t v[3], const Fr s[5]) {
         Fr val = (s[0] * var_vals[v[0]].pow_u64(5) + s[1] * var_vals[v[1]].pow_u64(5) +
                   s[2] * var_vals[v[2]].pow_u64(5) + s[3]) *
-                 (-s[4]).inverse();
+                 inv_cached(-s[4]);
         uint32_t o = add_input(val);
         push_gate(v[0], v[1], o, v[2]);
         sel(Q_HL) = s[0];
@@ -96,7 +106,7 @@ struct Composer {
     // hash.rs:76-120
     uint32_t partial_affine_transform_gate(const uint32_t v[3], const Fr s[5]) {
         Fr val = (s[0] * var_vals[v[0]].pow_u64(5) + s[1] * var_vals[v[1]] + s[2] * var_vals[v[2]] + s[3]) *
-                 (-s[4]).inverse();
+                 inv_cached(-s[4]);
         uint32_t o = add_input(val);
         push_gate(v[0], v[1], o, v[2]);
         sel(Q_HL) = s[0];

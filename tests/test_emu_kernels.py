@@ -1,0 +1,65 @@
+"""Runs the PRODUCT sources (kernels + host driver) under the CPU emulation layer of tests/emu and compares with
+the oracle.  This exercises indexing, protocol order and the limb algorithms without a GPU; the GPU parity tests
+(-m gpu) remain the real gate."""
+import numpy as np
+import pytest
+
+import oracle_lib
+
+ONE = np.array([8589934590, 6378425256633387010, 11064306276430008309, 1739710354780652911], dtype=np.uint64)
+
+
+@pytest.fixture(scope="module")
+def ctx(pkg, emu_lib):
+    c = pkg.ProverContext(8, emu_lib)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("logn", [1, 5, 9, 10, 12])
+def test_ntt_family(ctx, oracle, logn):
+    x = oracle.random_fr(1, 1 << logn)
+    for kind in range(4):
+        assert np.array_equal(ctx.ntt(kind, x), oracle.ntt(kind, x)), (logn, kind)
+
+
+def test_scans(ctx, oracle):
+    x = oracle.random_fr(3, 3000)
+    z = oracle.random_fr(4, 1)[0]
+    assert np.array_equal(ctx.poly_eval(x, z), oracle.poly_eval(x, z))
+    pp = ctx.prefix_product(x)
+    assert np.array_equal(pp[0], ONE)
+    assert np.array_equal(pp[1:], oracle.fr_op(2, pp[:-1].copy(), x[:-1].copy()))
+    q = ctx.poly_divide(x, z)
+    r = oracle.random_fr(5, 1)[0]
+    lhs = oracle.fr_op(1, oracle.poly_eval(x, r).reshape(1, 4), oracle.poly_eval(x, z).reshape(1, 4))
+    rhs = oracle.fr_op(2, oracle.poly_eval(q, r).reshape(1, 4), oracle.fr_op(1, r.reshape(1, 4), z.reshape(1, 4)))
+    assert np.array_equal(lhs, rhs)
+
+
+@pytest.mark.parametrize("n,wb", [(1, 0), (200, 5), (600, 9), (1024, 0)])
+def test_msm(ctx, oracle, n, wb):
+    pts, _ = oracle.srs(7, n)
+    sc = oracle.random_fr(2, n)
+    if n > 100:
+        sc[3] = 0
+        sc[4] = ONE
+        sc[5] = oracle.fr_op(6, ONE.reshape(1, 4))[0]
+        pts[10:20] = pts[10]
+        sc[10:20] = sc[10]
+    assert np.array_equal(ctx.msm_points(pts, sc, wb), oracle.msm(pts, sc))
+
+
+@pytest.mark.parametrize("n_lookup", [0, 12])
+def test_gen_proof_byte_identical_under_emulation(pkg, emu_lib, oracle, n_lookup):
+    oc = oracle_lib.OracleCircuit(oracle, 3, 42, 7, n_lookup)  # 3 hashes, N = 2^10
+    ref_proof, _ = oc.prove()
+    c = pkg.ProverContext(oc.log_n, emu_lib)
+    c.load_srs(oc.srs())
+    c.preprocess(oc.selector_evals(), oc.tables())
+    circ = pkg.make_circuit(oc.cs_n, oc.lookup_len, oc.pi_pos, oc.q_lookup(), oc.pi_canonical(), *oc.wires())
+    proof = c.prove(circ).to_words()
+    assert np.array_equal(proof, ref_proof)
+    assert oc.verify(proof)[0]
+    c.close()
+    oc.close()

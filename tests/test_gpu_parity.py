@@ -1,0 +1,166 @@
+"""GPU parity tests proper: every call goes through the C-ABI of libzprize_b200.so on a real device and is
+compared bit for bit with the CPU oracle (integer arithmetic: the bar is exact equality)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import oracle_lib
+
+pytestmark = pytest.mark.gpu
+
+ONE = np.array([8589934590, 6378425256633387010, 11064306276430008309, 1739710354780652911], dtype=np.uint64)
+
+
+@pytest.fixture(scope="module")
+def ctx16(pkg, gpu_lib):
+    c = pkg.ProverContext(16, gpu_lib)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("logn", [6, 9, 10, 13, 16, 18, 19])
+@pytest.mark.parametrize("kind", [0, 1, 2, 3])
+def test_ntt_matches_oracle(ctx16, oracle, logn, kind):
+    x = oracle.random_fr(1, 1 << logn)
+    assert np.array_equal(ctx16.ntt(kind, x), oracle.ntt(kind, x))
+
+
+def test_ntt_roundtrip_and_linearity_large(ctx16, oracle):
+    # size-independent properties at 2^22 (the HEIGHT=15 domain): iNTT(NTT(x)) = x, NTT(x + y) = NTT(x) + NTT(y)
+    n = 1 << 22
+    x, y = oracle.random_fr(11, n), oracle.random_fr(12, n)
+    fx = ctx16.ntt(0, x)
+    assert np.array_equal(ctx16.ntt(1, fx), x)
+    fy = ctx16.ntt(0, y)
+    assert np.array_equal(ctx16.ntt(0, oracle.fr_op(0, x, y)), oracle.fr_op(0, fx, fy))
+    cx = ctx16.ntt(2, x)
+    assert np.array_equal(ctx16.ntt(3, cx), x)
+    # spot-check 4 evaluations against Horner on the CPU
+    w, _, _ = np.zeros(4, np.uint64), None, None
+    fwd, inv, ninv = np.zeros(4, np.uint64), np.zeros(4, np.uint64), np.zeros(4, np.uint64)
+    oracle.lib.zpo_fr_root_of_unity(22, oracle_lib._p(fwd), oracle_lib._p(inv), oracle_lib._p(ninv))
+    pt = ONE.copy()
+    for i in range(3):
+        assert np.array_equal(fx[i], oracle.poly_eval(x, pt))
+        pt = oracle.fr_op(2, pt.reshape(1, 4), fwd.reshape(1, 4))[0]
+
+
+def test_scan_eval_divide(ctx16, oracle):
+    n = 70001
+    x = oracle.random_fr(3, n)
+    z = oracle.random_fr(4, 1)[0]
+    assert np.array_equal(ctx16.poly_eval(x, z), oracle.poly_eval(x, z))
+    q = ctx16.poly_divide(x, z)
+    # p(X) - p(z) = q(X) (X - z): check at a random point
+    r = oracle.random_fr(5, 1)[0]
+    lhs = oracle.fr_op(1, oracle.poly_eval(x, r).reshape(1, 4), oracle.poly_eval(x, z).reshape(1, 4))
+    rhs = oracle.fr_op(2, oracle.poly_eval(q, r).reshape(1, 4), oracle.fr_op(1, r.reshape(1, 4), z.reshape(1, 4)))
+    assert np.array_equal(lhs, rhs)
+    pp = ctx16.prefix_product(x)
+    assert np.array_equal(pp[0], ONE)
+    # telescoping: pp[i+1] = pp[i] * x[i]
+    assert np.array_equal(pp[1:], oracle.fr_op(2, pp[:-1].copy(), x[:-1].copy()))
+
+
+@pytest.mark.parametrize("n,wb", [(1, 0), (37, 0), (1 << 10, 0), (1 << 10, 5), (1 << 12, 0), (1 << 14, 13), (1 << 16, 0)])
+def test_msm_matches_oracle(ctx16, oracle, n, wb):
+    pts, _ = oracle.srs(7, n)
+    sc = oracle.random_fr(2, n)
+    assert np.array_equal(ctx16.msm_points(pts, sc, wb), oracle.msm(pts, sc))
+
+
+def test_msm_adversarial_scalars(ctx16, oracle):
+    n = 1 << 10
+    pts, _ = oracle.srs(7, n)
+    sc = oracle.random_fr(2, n)
+    minus_one = oracle.fr_op(6, ONE.reshape(1, 4))[0]
+    sc[0:64] = 0            # zeros
+    sc[64:128] = ONE        # ones
+    sc[128:192] = minus_one  # r - 1: every window digit at its extreme
+    pts[200:264] = pts[200]  # repeated points (forces the doubling branch of the bucket add)
+    sc[200:264] = sc[200]
+    assert np.array_equal(ctx16.msm_points(pts, sc), oracle.msm(pts, sc))
+    z = np.zeros_like(sc)
+    out = ctx16.msm_points(pts, z)
+    assert not out[:6].any() and np.array_equal(out[6:], oracle_fq_one(oracle))
+
+
+def oracle_fq_one(oracle):
+    m, one, rr = (np.zeros(6, np.uint64) for _ in range(3))
+    inv = ctypes.c_uint64()
+    oracle.lib.zpo_fq_constants(oracle_lib._p(m), oracle_lib._p(one), oracle_lib._p(rr),
+                                ctypes.cast(ctypes.byref(inv), oracle_lib.u64p))
+    return one
+
+
+def test_device_srs_matches_oracle(pkg, gpu_lib, oracle):
+    ctx = pkg.ProverContext(10, gpu_lib)
+    pts, tau = oracle.srs(7, 1 << 10)
+    ctx.generate_srs(tau)
+    assert np.array_equal(ctx.read_srs(), pts)
+    ctx.close()
+
+
+def _prove_and_compare(pkg, lib, oracle, height, n_lookup, use_host_pk):
+    oc = oracle_lib.OracleCircuit(oracle, height, 42, 7, n_lookup)
+    ref_proof, _ = oc.prove()
+    ctx = pkg.ProverContext(oc.log_n, lib)
+    ctx.load_srs(oc.srs())
+    keep = None
+    if use_host_pk:
+        co, ev = oc.pk_coeffs(), oc.pk_evals()
+        names = pkg.PK_POLY_NAMES + pkg.PK_SIGMA_NAMES
+        keep = (co, ev, oc.tables(), oc.linear_evaluations(), oc.v_h_coset_8n())
+        pk = pkg.make_prover_key(dict(zip(names, co)), dict(zip(names, ev)), keep[2], keep[3], keep[4])
+        ctx.load_pk(pk)
+    else:
+        ctx.preprocess(oc.selector_evals(), oc.tables())
+    circ = pkg.make_circuit(oc.cs_n, oc.lookup_len, oc.pi_pos, oc.q_lookup(), oc.pi_canonical(), *oc.wires())
+    proof = ctx.prove(circ).to_words()
+    assert np.array_equal(proof, ref_proof)
+    ok, _ = oc.verify(proof)
+    assert ok
+    # verifier key computed on the device equals the oracle's
+    ctx.close()
+    oc.close()
+
+
+@pytest.mark.parametrize("height,n_lookup,use_host_pk", [(4, 0, False), (4, 0, True), (4, 24, False), (4, 24, True),
+                                                        (6, 0, False)])
+def test_gen_proof_byte_identical(pkg, gpu_lib, oracle, height, n_lookup, use_host_pk):
+    _prove_and_compare(pkg, gpu_lib, oracle, height, n_lookup, use_host_pk)
+
+
+def test_drop_in_gen_proof_symbol(pkg, gpu_lib, oracle):
+    """The reference's own FFI call: by-value structs in, ProofC by value out (lib.rs:237-239)."""
+    oc = oracle_lib.OracleCircuit(oracle, 4, 42, 7, 0)
+    ref_proof, _ = oc.prove()
+    names = pkg.PK_POLY_NAMES + pkg.PK_SIGMA_NAMES
+    co, ev, tb = oc.pk_coeffs(), oc.pk_evals(), oc.tables()
+    le, vh = oc.linear_evaluations(), oc.v_h_coset_8n()
+    pk = pkg.make_prover_key(dict(zip(names, co)), dict(zip(names, ev)), tb, le, vh)
+    # the reference passes dangling pointers for the coefficient arrays of identically-zero selectors
+    for nm in ["q_m", "range_selector", "logic_selector", "fixed_group_add_selector", "variable_group_add_selector", "q_lookup"]:
+        setattr(pk, nm + "_coeffs", ctypes.cast(0xdead0000, pkg.u64p))
+    srs = oc.srs()
+    ck = pkg.CommitKeyC()
+    ck.powers_of_g = pkg.as_u64p(srs)
+    circ = pkg.make_circuit(oc.cs_n, oc.lookup_len, oc.pi_pos, oc.q_lookup(), oc.pi_canonical(), *oc.wires())
+    for _ in range(2):  # second call hits the resident-key cache
+        proof = pkg.gen_proof(circ, pk, ck, gpu_lib)
+        assert np.array_equal(proof.to_words(), ref_proof)
+    oc.close()
+
+
+def test_verifier_key_and_known_tau(pkg, gpu_lib, oracle):
+    oc = oracle_lib.OracleCircuit(oracle, 4, 42, 7, 0)
+    ctx = pkg.ProverContext(oc.log_n, gpu_lib)
+    ctx.load_srs(oc.srs())
+    ctx.preprocess(oc.selector_evals(), oc.tables())
+    vk = ctx.verifier_key()
+    co = oc.pk_coeffs()
+    for i in [1, 3, 5, 6, 9, 15, 18]:
+        assert np.array_equal(vk[i], oc.commit_with_tau(co[i]))  # commit(p) == [p(tau)] G
+    ctx.close()
+    oc.close()
