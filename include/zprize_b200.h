@@ -117,6 +117,11 @@ int zp_device_available(void);
 /* Context for domain size N = 2^log_n on the current CUDA device. NULL on error. */
 zp_prover* zp_prover_create(int log_n);
 void zp_prover_destroy(zp_prover* p);
+/* Run all work of this context on the caller's CUDA stream (a cudaStream_t, e.g. torch's current stream)
+ * instead of the context's own stream, so that the caller's events bracket the prover's kernels. */
+int zp_prover_set_stream(zp_prover* p, void* cuda_stream);
+/* cudaProfilerStart (1) / cudaProfilerStop (0): lets `ncu --profile-from-start off` capture one proof. */
+int zp_profiler_range(int start);
 /* transcript label; default "Merkle tree" (gen_proof.cuh:19-20) */
 int zp_prover_set_label(zp_prover* p, const char* label);
 /* SRS: n_points affine points (CommitKeyC.powers_of_g layout), n_points >= N. */
@@ -140,6 +145,21 @@ int zp_prover_preprocess(zp_prover* p, const uint64_t* const* selector_evals, co
 int zp_prover_verifier_key(zp_prover* p, uint64_t* out_commitments);
 /* One proof with the resident key.  Host pointers in `circuit`; returns 0 on success. */
 int zp_prover_prove(zp_prover* p, const CircuitC* circuit, ProofC* out);
+/* Split form of zp_prover_prove for kernel-only timing: upload the witness once (host -> HBM), then prove
+ * any number of times with every input already resident. */
+int zp_prover_upload_witness(zp_prover* p, const CircuitC* circuit);
+int zp_prover_prove_resident(zp_prover* p, ProofC* out);
+/* Per-proof statistics of the MSM bucket-accumulation kernel (the dominant kernel): enable, then after a
+ * proof read out4 = { sum of kernel ms, launches, algorithmic 32-bit multiply-adds (10*588*M*W),
+ * sum of all MSM kernel ms }. */
+int zp_prover_collect_msm_stats(zp_prover* p, int enable);
+int zp_prover_msm_stats(zp_prover* p, double* out4);
+/* Multi-GPU sharding of the commitments (one process per GPU, every rank holds the same key and witness):
+ * rank r computes each MSM over points [r*ceil(n/world), (r+1)*ceil(n/world)) only and the partial sums
+ * are exchanged with `allgather(user, send, recv, bytes_per_rank)` — recv holds world * bytes_per_rank
+ * bytes in rank order; return 0 on success.  world = 1 disables sharding. */
+typedef int (*zp_allgather_fn)(void* user, const void* send, void* recv, size_t bytes_per_rank);
+int zp_prover_set_shard(zp_prover* p, int rank, int world, zp_allgather_fn allgather, void* user);
 /* Device-milliseconds of the phases of the last proof: [0] total, [1] NTT, [2] MSM, [3] quotient,
  * [4] other (CUDA events on the prover's stream). */
 int zp_prover_last_timing(zp_prover* p, double* out_ms, int n);

@@ -3,6 +3,9 @@
 #include <chrono>
 #include <map>
 #include <mutex>
+#ifndef ZP_EMU
+#include <cuda_profiler_api.h>
+#endif
 
 using namespace zp;
 
@@ -59,6 +62,17 @@ void zp_prover_destroy(zp_prover* p) {
     }
     delete P(p);
 }
+int zp_prover_set_stream(zp_prover* p, void* cuda_stream) {
+    return guard([&] { P(p)->set_stream(reinterpret_cast<cudaStream_t>(cuda_stream)); });
+}
+int zp_profiler_range(int start) {
+#ifndef ZP_EMU
+    return start ? (int)cudaProfilerStart() : (int)cudaProfilerStop();
+#else
+    (void)start;
+    return 0;
+#endif
+}
 int zp_prover_set_label(zp_prover* p, const char* label) { return guard([&] { P(p)->label = label; }); }
 int zp_prover_load_srs(zp_prover* p, const uint64_t* pts, size_t n) { return guard([&] { P(p)->load_srs(pts, n); }); }
 int zp_prover_generate_srs(zp_prover* p, const uint64_t* tau, size_t n) {
@@ -83,6 +97,28 @@ int zp_prover_preprocess(zp_prover* p, const uint64_t* const* selector_evals, co
 }
 int zp_prover_verifier_key(zp_prover* p, uint64_t* out) { return guard([&] { P(p)->verifier_key(out); }); }
 int zp_prover_prove(zp_prover* p, const CircuitC* c, ProofC* out) { return guard([&] { P(p)->prove(*c, out); }); }
+int zp_prover_upload_witness(zp_prover* p, const CircuitC* c) { return guard([&] { P(p)->upload_witness(*c); }); }
+int zp_prover_prove_resident(zp_prover* p, ProofC* out) { return guard([&] { P(p)->prove_resident(out); }); }
+int zp_prover_collect_msm_stats(zp_prover* p, int enable) { return guard([&] { P(p)->collect_msm_stats = enable != 0; }); }
+int zp_prover_msm_stats(zp_prover* p, double* out4) {
+    return guard([&] {
+        Prover* pr = P(p);
+        out4[0] = pr->msm_acc_ms;
+        out4[1] = pr->msm_launches;
+        out4[2] = pr->msm_mads;
+        out4[3] = pr->msm_all_ms;
+    });
+}
+int zp_prover_set_shard(zp_prover* p, int rank, int world, zp_allgather_fn fn, void* user) {
+    return guard([&] {
+        if (world < 1 || rank < 0 || rank >= world) throw std::runtime_error("zp_prover_set_shard: bad rank/world");
+        Prover* pr = P(p);
+        pr->shard_rank = rank;
+        pr->shard_world = world;
+        pr->allgather = fn;
+        pr->allgather_user = user;
+    });
+}
 int zp_prover_last_timing(zp_prover* p, double* out_ms, int n) {
     return guard([&] {
         for (int i = 0; i < n && i < 5; i++) out_ms[i] = P(p)->last_ms[i];

@@ -4,7 +4,8 @@
 //   1. digits    : Montgomery scalar -> canonical -> signed c-bit digits, per-(window,bucket) histogram
 //   2. scan      : exclusive scan of the histogram (bucket start offsets), one CTA
 //   3. scatter   : counting-sort the point indices into (window,bucket) runs (atomic cursor per bucket)
-//   4. accumulate: one thread per bucket, XYZZ mixed additions over its run (the IMAD-bound hot loop)
+//   4. accumulate: one thread per work segment (<= 2x mean bucket load) of a bucket, XYZZ mixed additions
+//                  (the IMAD-bound hot loop); long buckets are split so no digit distribution serialises
 //   5. reduce    : per window and bucket group, running-sum reduction  sum_b (b+1) * B_b  + tree in smem
 //   host         : fold 8 partials per window, Horner over windows (256 doublings), to affine
 // Order inside a bucket is not deterministic (atomics) but the group sum is exact, so the affine
@@ -32,7 +33,12 @@ void MsmWorkspace::reserve(size_t n, const MsmConfig& cfg) {
     if (sorted.n < wn) sorted.alloc(wn);
     if (start.n < wb + 1) start.alloc(wb + 1);
     if (cursor.n < wb) cursor.alloc(wb);
-    if (buckets.n < wb) buckets.alloc(wb);
+    if (seg_start.n < wb + 1) seg_start.alloc(wb + 1);
+    if (seg_cnt.n < wb) seg_cnt.alloc(wb);
+    size_t mean = (n + cfg.nbuckets - 1) / cfg.nbuckets;
+    seg = 2 * mean < 32 ? 32 : 2 * mean;
+    max_segs = wn / seg + wb + 1;
+    if (segs.n < max_segs) segs.alloc(max_segs);
     size_t np = (size_t)cfg.nwin * MSM_REDUCE_GROUPS;
     if (partial.n < np) partial.alloc(np);
     if (partial_host.size() < np) partial_host.resize(np);
@@ -127,35 +133,62 @@ ZP_D xyzz_t load_xyzz(const xyzz_t* p) {
     return r;
 }
 
-__global__ void __launch_bounds__(128) msm_accumulate_kernel(const affine_t* __restrict__ points, const uint32_t* __restrict__ sorted,
-                                                             const uint32_t* __restrict__ start, const uint32_t* __restrict__ endp,
-                                                             size_t nb, xyzz_t* __restrict__ buckets) {
+// Work segments: a bucket with cnt points is split into ceil(cnt / seg) segments so that one thread never
+// walks more than `seg` points, whatever the digit distribution (short top window, repeated scalars …).
+__global__ void __launch_bounds__(256) msm_segcount_kernel(const uint32_t* __restrict__ start, const uint32_t* __restrict__ endp,
+                                                           size_t nb, uint32_t seg, uint32_t* __restrict__ seg_cnt) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nb) return;
-    uint32_t lo = start[t], hi = endp[t];
+    uint32_t c = endp[t] - start[t];
+    seg_cnt[t] = (c + seg - 1) / seg;
+}
+
+// One thread per work segment: XYZZ mixed additions over <= seg points of one bucket.
+__global__ void __launch_bounds__(128) msm_accumulate_kernel(const affine_t* __restrict__ points, const uint32_t* __restrict__ sorted,
+                                                             const uint32_t* __restrict__ start, const uint32_t* __restrict__ endp,
+                                                             const uint32_t* __restrict__ seg_start, size_t nb, uint32_t seg,
+                                                             xyzz_t* __restrict__ segs) {
+    size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= seg_start[nb]) return;
+    // bucket b with seg_start[b] <= s < seg_start[b+1]
+    size_t lo_b = 0, hi_b = nb;
+    while (hi_b - lo_b > 1) {
+        size_t mid = (lo_b + hi_b) >> 1;
+        if (seg_start[mid] <= (uint32_t)s) lo_b = mid; else hi_b = mid;
+    }
+    uint32_t k0 = start[lo_b] + ((uint32_t)s - seg_start[lo_b]) * seg;
+    uint32_t k1 = k0 + seg < endp[lo_b] ? k0 + seg : endp[lo_b];
     xyzz_t acc = xyzz_t::infinity();
-    for (uint32_t k = lo; k < hi; k++) {
+    for (uint32_t k = k0; k < k1; k++) {
         uint32_t e = sorted[k];
         affine_t p = load_affine(&points[e & 0x7fffffffu]);
         if (e >> 31) p.y = p.y.neg();
         acc.add_affine(p.x, p.y);
     }
-    store_xyzz(&buckets[t], acc);
+    store_xyzz(&segs[s], acc);
+}
+
+ZP_D xyzz_t load_bucket(const xyzz_t* __restrict__ segs, const uint32_t* __restrict__ seg_start, size_t b) {
+    uint32_t s0 = seg_start[b], s1 = seg_start[b + 1];
+    if (s0 == s1) return xyzz_t::infinity();
+    xyzz_t acc = load_xyzz(&segs[s0]);
+    for (uint32_t s = s0 + 1; s < s1; s++) acc.add(load_xyzz(&segs[s]));
+    return acc;
 }
 
 // One CTA per (window, bucket group).  partial[w * G + g] = sum_{b in group} (b + 1) * bucket[w][b]
-__global__ void __launch_bounds__(128) msm_reduce_kernel(const xyzz_t* __restrict__ buckets, int nbuckets, int groups,
-                                                         xyzz_t* __restrict__ partial) {
+__global__ void __launch_bounds__(128) msm_reduce_kernel(const xyzz_t* __restrict__ segs, const uint32_t* __restrict__ seg_start,
+                                                         int nbuckets, int groups, xyzz_t* __restrict__ partial) {
     ZP_DYN_SMEM(xyzz_t, sm);
     const int w = blockIdx.x / groups, g = blockIdx.x % groups;
     const int bg = nbuckets / groups;          // buckets per group
     const int T = blockDim.x;
     const int L = bg / T;                      // buckets per thread (host guarantees divisibility, L >= 1)
     const int j0 = g * bg + threadIdx.x * L;   // first bucket of this thread (weight j0 + 1)
-    const xyzz_t* B = buckets + (size_t)w * nbuckets;
+    const size_t B0 = (size_t)w * nbuckets;
     xyzz_t run = xyzz_t::infinity(), sum = xyzz_t::infinity();
     for (int j = j0 + L - 1; j >= j0; j--) {
-        xyzz_t b = load_xyzz(&B[j]);
+        xyzz_t b = load_bucket(segs, seg_start, B0 + j);
         run.add(b);
         sum.add(run);
     }
@@ -202,16 +235,19 @@ void msm_launch(MsmWorkspace& ws, const MsmConfig& cfg, const affine_t* points, 
         ZP_LAUNCH(msm_scatter_kernel, dim3((unsigned)((n + 255) / 256), cfg.nwin), dim3(256), 0, st, ws.digits.p, n, cfg.nwin,
                   cfg.nbuckets, ws.cursor.p, ws.sorted.p);
     }
+    ZP_LAUNCH(msm_segcount_kernel, dim3((unsigned)((wb + 255) / 256)), dim3(256), 0, st, ws.start.p, ws.cursor.p, wb,
+              (uint32_t)ws.seg, ws.seg_cnt.p);
+    ZP_LAUNCH(msm_scan_kernel, dim3(1), dim3(1024), 0, st, ws.seg_cnt.p, ws.seg_start.p, wb);
     mark(3);
-    ZP_LAUNCH(msm_accumulate_kernel, dim3((unsigned)((wb + 127) / 128)), dim3(128), 0, st, points, ws.sorted.p, ws.start.p,
-              ws.cursor.p, wb, ws.buckets.p);
+    ZP_LAUNCH(msm_accumulate_kernel, dim3((unsigned)((ws.max_segs + 127) / 128)), dim3(128), 0, st, points, ws.sorted.p,
+              ws.start.p, ws.cursor.p, ws.seg_start.p, wb, (uint32_t)ws.seg, ws.segs.p);
     mark(4);
     int groups = MSM_REDUCE_GROUPS;
     while (cfg.nbuckets / groups < 1) groups >>= 1;
     int bg = cfg.nbuckets / groups;
     int T = bg < 128 ? bg : 128;
-    ZP_LAUNCH(msm_reduce_kernel, dim3(cfg.nwin * groups), dim3(T), (size_t)T * sizeof(xyzz_t), st, ws.buckets.p, cfg.nbuckets,
-              groups, ws.partial.p);
+    ZP_LAUNCH(msm_reduce_kernel, dim3(cfg.nwin * groups), dim3(T), (size_t)T * sizeof(xyzz_t), st, ws.segs.p, ws.seg_start.p,
+              cfg.nbuckets, groups, ws.partial.p);
     mark(5);
     ZP_CUDA(cudaMemcpyAsync(ws.partial_host.data(), ws.partial.p, (size_t)cfg.nwin * groups * sizeof(xyzz_t),
                             cudaMemcpyDeviceToHost, st));

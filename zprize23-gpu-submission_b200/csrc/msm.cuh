@@ -20,7 +20,11 @@ struct MsmWorkspace {
     DevBuf<uint32_t> sorted;   // [<= nwin*n] point index | sign << 31, grouped by (window, bucket)
     DevBuf<uint32_t> start;    // [nwin*nbuckets + 1] exclusive scan of bucket sizes
     DevBuf<uint32_t> cursor;   // [nwin*nbuckets]     running insert position; == bucket end after the scatter
-    DevBuf<xyzz_t> buckets;    // [nwin*nbuckets]
+    DevBuf<uint32_t> seg_start;// [nwin*nbuckets + 1] exclusive scan of ceil(bucket size / seg) (work segments)
+    DevBuf<uint32_t> seg_cnt;  // [nwin*nbuckets]
+    DevBuf<xyzz_t> segs;       // [<= nwin*n/seg + nwin*nbuckets] partial sum of each work segment
+    size_t seg = 0;            // points per work segment (2x the mean bucket load, >= 32)
+    size_t max_segs = 0;
     DevBuf<xyzz_t> partial;    // [nwin * MSM_REDUCE_GROUPS]
     std::vector<xyzz_t> partial_host;
     // optional per-kernel timing (bench only): digits, scan, scatter, accumulate, reduce

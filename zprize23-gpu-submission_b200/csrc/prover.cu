@@ -75,7 +75,13 @@ Prover::Prover(int logn_) : logn(logn_), n((size_t)1 << logn_), n8((size_t)8 << 
     ZP_CUDA(cudaStreamSynchronize(st));
 }
 Prover::~Prover() {
-    if (st) cudaStreamDestroy(st);
+    if (st && own_stream) cudaStreamDestroy(st);
+}
+void Prover::set_stream(cudaStream_t s) {
+    ZP_CUDA(cudaStreamSynchronize(st));
+    if (st && own_stream) cudaStreamDestroy(st);
+    st = s;
+    own_stream = false;
 }
 
 void Prover::ensure_work_buffers(bool lookup) {
@@ -288,9 +294,29 @@ void Prover::commit(const fr_t* coeffs_dev, size_t ncoef, CommitmentC* out, Fq* 
     if (!coeffs_dev || ncoef == 0) {
         host::G1::infinity().to_affine(x, y, inf);
     } else {
-        MsmConfig cfg = msm_config_for(ncoef);
-        msm_launch(MW, cfg, srs.p, coeffs_dev, ncoef, st);
-        host::G1 r = msm_collect(MW, cfg, st);
+        // point-range shard of this rank (the whole range when world == 1)
+        size_t chunk = (ncoef + shard_world - 1) / shard_world;
+        size_t lo = std::min(ncoef, (size_t)shard_rank * chunk), hi = std::min(ncoef, lo + chunk);
+        host::G1 r = host::G1::infinity();
+        if (hi > lo) {
+            MsmConfig cfg = msm_config_for(hi - lo);
+            msm_launch(MW, cfg, srs.p + lo, coeffs_dev + lo, hi - lo, st);
+            r = msm_collect(MW, cfg, st);
+            if (MW.timing) {
+                msm_acc_ms += MW.last_ms[3];
+                for (int k = 0; k < 5; k++) msm_all_ms += MW.last_ms[k];
+                msm_mads += 10.0 * 588.0 * (double)(hi - lo) * cfg.nwin;  // 10 * 588 * M * W
+                msm_launches++;
+            }
+        }
+        if (shard_world > 1) {
+            if (!allgather) throw std::runtime_error("commit: sharded prover without an all-gather callback");
+            std::vector<host::G1> all(shard_world);
+            if (allgather(allgather_user, &r, all.data(), sizeof(host::G1)) != 0)
+                throw std::runtime_error("commit: all-gather of MSM partial sums failed");
+            r = host::G1::infinity();
+            for (int k = 0; k < shard_world; k++) r.add(all[k]);
+        }
         r.to_affine(x, y, inf);
     }
     memcpy(out->x, x.v, 48);
@@ -357,18 +383,10 @@ static inline fr_t D(const Fr& a) { return host::to_dev(a); }
 static inline Fr H(const fr_t& a) { return host::to_host(a); }
 static void put_fr(uint64_t* dst, const Fr& a) { memcpy(dst, a.v, 32); }
 
-void Prover::prove(const CircuitC& c, ProofC* out) {
-    if (!have_pk) throw std::runtime_error("zp_prover_prove: no prover key loaded");
-    if (!srs.p) throw std::runtime_error("zp_prover_prove: no SRS loaded");
+void Prover::upload_witness(const CircuitC& c) {
     if (c.n > n || c.n == 0) throw std::runtime_error("zp_prover_prove: circuit size does not fit the domain");
-    PhaseTimer timer(st);
-    g_timer = &timer;
-    struct TimerGuard { ~TimerGuard() { g_timer = nullptr; } } timer_guard;
-    int total_id = timer.begin(CAT_TOTAL);
-    memset(out, 0, sizeof(ProofC));
     const size_t cn = (size_t)c.n;
-
-    // ---- 0. witness upload + transcript start (gen_proof.cuh:11-22)
+    // ---- 0. witness upload (gen_proof.cuh:11-17, load.cu:311-345)
     ensure_work_buffers(false);
     const uint64_t* wires[4] = {c.w_l, c.w_r, c.w_o, c.w_4};
     for (int k = 0; k < 4; k++) {
@@ -376,13 +394,40 @@ void Prover::prove(const CircuitC& c, ProofC* out) {
         if (cn < n) ZP_CUDA(cudaMemsetAsync(w_ev[k].p + cn, 0, (n - cn) * sizeof(fr_t), st));
     }
     ZP_CUDA(cudaMemcpyAsync(qlk_ev.p, c.q_lookup, cn * sizeof(fr_t), cudaMemcpyHostToDevice, st));
-    bool lookup_on = !(table_zero && all_zero(PS, qlk_ev.p, cn, st));
-    if (lookup_on) ensure_work_buffers(true);
+    wit_lookup_on = !(table_zero && all_zero(PS, qlk_ev.p, cn, st));
+    if (wit_lookup_on) ensure_work_buffers(true);
+    wit_n = cn;
+    memcpy(wit_pi, c.pi, 32);
+    wit_pi_pos = c.intended_pi_pos;
+}
+
+void Prover::prove(const CircuitC& c, ProofC* out) {
+    if (!have_pk) throw std::runtime_error("zp_prover_prove: no prover key loaded");
+    if (!srs.p) throw std::runtime_error("zp_prover_prove: no SRS loaded");
+    upload_witness(c);
+    prove_resident(out);
+}
+
+void Prover::prove_resident(ProofC* out) {
+    if (!have_pk) throw std::runtime_error("zp_prover_prove: no prover key loaded");
+    if (!srs.p) throw std::runtime_error("zp_prover_prove: no SRS loaded");
+    if (!wit_n) throw std::runtime_error("zp_prover_prove_resident: no witness uploaded");
+    PhaseTimer timer(st);
+    g_timer = &timer;
+    struct TimerGuard { ~TimerGuard() { g_timer = nullptr; } } timer_guard;
+    int total_id = timer.begin(CAT_TOTAL);
+    memset(out, 0, sizeof(ProofC));
+    const size_t cn = wit_n;
+    const bool lookup_on = wit_lookup_on;
+    msm_acc_ms = msm_all_ms = msm_mads = 0;
+    msm_launches = 0;
+    MW.timing = collect_msm_stats;
+    struct TimingOff { MsmWorkspace& w; ~TimingOff() { w.timing = false; } } timing_off{MW};
 
     MerlinTranscript tr(label);
-    Fr pi_val = Fr::from_canonical(c.pi);  // CircuitC.pi is canonical (prover.rs:721-725)
+    Fr pi_val = Fr::from_canonical(wit_pi);  // CircuitC.pi is canonical (prover.rs:721-725)
     std::vector<std::pair<uint64_t, Fr>> pis;
-    if (!pi_val.is_zero()) pis.push_back({c.intended_pi_pos, pi_val});  // PublicInputs keeps non-zero values only
+    if (!pi_val.is_zero()) pis.push_back({wit_pi_pos, pi_val});  // PublicInputs keeps non-zero values only
     tr.append_public_inputs("pi", pis);
 
     // ---- 1. witness polynomials (prover.rs:192-228)
@@ -480,7 +525,7 @@ void Prover::prove(const CircuitC& c, ProofC* out) {
     // public-input polynomial (pi.rs:103-116)
     ZP_CUDA(cudaMemsetAsync(num.p, 0, n * sizeof(fr_t), st));
     fr_t pi_dev = D(pi_val);
-    if (!pis.empty()) ZP_CUDA(cudaMemcpyAsync(num.p + c.intended_pi_pos, &pi_dev, sizeof(fr_t), cudaMemcpyHostToDevice, st));
+    if (!pis.empty()) ZP_CUDA(cudaMemcpyAsync(num.p + wit_pi_pos, &pi_dev, sizeof(fr_t), cudaMemcpyHostToDevice, st));
     { Scope s(CAT_NTT); ntt_run(T, NS, NTT_INV, logn, num.p, n, pi_poly.p, st); }
 
     // ---- 4. quotient polynomial (prover.rs:402-489, quotient_poly.rs:34-206)

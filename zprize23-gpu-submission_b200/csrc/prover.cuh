@@ -23,6 +23,7 @@ struct Prover {
     int logn;
     size_t n, n8;
     cudaStream_t st = 0;
+    bool own_stream = true;
     std::string label = "Merkle tree";
     NttTables T;
     NttScratch NS;
@@ -47,9 +48,26 @@ struct Prover {
     DevBuf<fr_t> pi_poly, pi8, quot, t_poly;
     DevBuf<fr_t> num, den, lin, comb, wit;
     double last_ms[5] = {0, 0, 0, 0, 0};
+    // witness currently resident in w_ev / qlk_ev (set by upload_witness)
+    size_t wit_n = 0;
+    uint64_t wit_pi[4] = {0, 0, 0, 0};
+    uint64_t wit_pi_pos = 0;
+    bool wit_lookup_on = false;
+    // per-proof MSM statistics (bucket-accumulation kernel, the dominant kernel of gen_proof)
+    bool collect_msm_stats = false;
+    double msm_acc_ms = 0, msm_all_ms = 0, msm_mads = 0;
+    int msm_launches = 0;
+
+    // multi-GPU: every rank runs the whole protocol on identical inputs, but each KZG commitment's MSM is
+    // sharded by point range; the per-rank partial sums (one XYZZ point, 192 B) are exchanged through the
+    // caller-supplied all-gather (torch.distributed / NCCL in bench.py) and folded in rank order.
+    int shard_rank = 0, shard_world = 1;
+    zp_allgather_fn allgather = nullptr;
+    void* allgather_user = nullptr;
 
     explicit Prover(int logn_);
     ~Prover();
+    void set_stream(cudaStream_t s);
     void ensure_work_buffers(bool lookup);
     void load_srs(const uint64_t* pts, size_t npts);
     void generate_srs(const fr_t& tau, size_t npts);
@@ -57,6 +75,8 @@ struct Prover {
     void preprocess(const uint64_t* const* selector_evals, const uint64_t* const* tables);
     void finish_pk();
     void verifier_key(uint64_t* out23);
+    void upload_witness(const CircuitC& c);
+    void prove_resident(ProofC* out);
     void prove(const CircuitC& c, ProofC* out);
 
     // commit to n coefficients (Montgomery) on the device; returns affine point (host)

@@ -98,6 +98,10 @@ class CommitKeyC(ctypes.Structure):  # lib.rs:225-229
 assert ctypes.sizeof(ProofC) == 2656 and ctypes.sizeof(ProverKeyC) == 44 * 8 and ctypes.sizeof(CircuitC) == 72
 
 
+# int (*zp_allgather_fn)(void* user, const void* send, void* recv, size_t bytes_per_rank)
+ALLGATHER_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t)
+
+
 class ZprizeError(RuntimeError):
     pass
 
@@ -125,6 +129,8 @@ def load_library(path=None):
         "zp_prover_create": (vp, [ci]),
         "zp_prover_destroy": (None, [vp]),
         "zp_prover_set_label": (ci, [vp, ctypes.c_char_p]),
+        "zp_profiler_range": (ci, [ci]),
+        "zp_prover_set_stream": (ci, [vp, vp]),
         "zp_prover_load_srs": (ci, [vp, u64p, cs]),
         "zp_prover_generate_srs": (ci, [vp, u64p, cs]),
         "zp_prover_read_srs": (ci, [vp, u64p, cs]),
@@ -133,6 +139,11 @@ def load_library(path=None):
         "zp_prover_verifier_key": (ci, [vp, u64p]),
         "zp_prover_prove": (ci, [vp, ctypes.POINTER(CircuitC), ctypes.POINTER(ProofC)]),
         "zp_prover_last_timing": (ci, [vp, dp, ci]),
+        "zp_prover_upload_witness": (ci, [vp, ctypes.POINTER(CircuitC)]),
+        "zp_prover_prove_resident": (ci, [vp, ctypes.POINTER(ProofC)]),
+        "zp_prover_collect_msm_stats": (ci, [vp, ci]),
+        "zp_prover_msm_stats": (ci, [vp, dp]),
+        "zp_prover_set_shard": (ci, [vp, ci, ci, ALLGATHER_FN, vp]),
         "zp_ntt_host": (ci, [vp, ci, ci, u64p, u64p]),
         "zp_msm_host": (ci, [vp, u64p, cs, u64p]),
         "zp_msm_points_host": (ci, [vp, u64p, u64p, cs, ci, u64p]),
@@ -157,9 +168,10 @@ def load_library(path=None):
 
 
 EXPORTED_SYMBOLS = ["gen_proof", "zp_last_error", "zp_launch_count", "zp_device_available", "zp_prover_create",
-                    "zp_prover_destroy", "zp_prover_set_label", "zp_prover_load_srs", "zp_prover_generate_srs",
+                    "zp_prover_destroy", "zp_prover_set_label", "zp_profiler_range", "zp_prover_set_stream", "zp_prover_load_srs", "zp_prover_generate_srs",
                     "zp_prover_read_srs", "zp_prover_load_pk", "zp_prover_preprocess", "zp_prover_verifier_key",
-                    "zp_prover_prove", "zp_prover_last_timing", "zp_ntt_host", "zp_msm_host", "zp_msm_points_host",
+                    "zp_prover_prove", "zp_prover_last_timing", "zp_prover_upload_witness", "zp_prover_prove_resident",
+                    "zp_prover_collect_msm_stats", "zp_prover_msm_stats", "zp_prover_set_shard", "zp_ntt_host", "zp_msm_host", "zp_msm_points_host",
                     "zp_poly_eval_host", "zp_poly_divide_host", "zp_prefix_product_host", "zp_bench_alloc",
                     "zp_bench_upload", "zp_bench_download", "zp_bench_ntt", "zp_bench_msm", "zp_bench_msm_breakdown",
                     "zp_bench_int_pipe"]
@@ -231,6 +243,9 @@ class ProverContext:
         if rc != 0:
             raise ZprizeError(self.lib.zp_last_error().decode())
 
+    def set_stream(self, cuda_stream):
+        self._ck(self.lib.zp_prover_set_stream(self.h, ctypes.c_void_p(cuda_stream)))
+
     def set_label(self, label):
         self._ck(self.lib.zp_prover_set_label(self.h, label))
 
@@ -267,6 +282,37 @@ class ProverContext:
         proof = ProofC()
         self._ck(self.lib.zp_prover_prove(self.h, ctypes.byref(circuit), ctypes.byref(proof)))
         return proof
+
+    def upload_witness(self, circuit):
+        self._ck(self.lib.zp_prover_upload_witness(self.h, ctypes.byref(circuit)))
+
+    def prove_resident(self):
+        proof = ProofC()
+        self._ck(self.lib.zp_prover_prove_resident(self.h, ctypes.byref(proof)))
+        return proof
+
+    def collect_msm_stats(self, enable=True):
+        self._ck(self.lib.zp_prover_collect_msm_stats(self.h, 1 if enable else 0))
+
+    def msm_stats(self):
+        out = (ctypes.c_double * 4)()
+        self._ck(self.lib.zp_prover_msm_stats(self.h, out))
+        return {"accumulate_ms": out[0], "launches": int(out[1]), "algorithmic_mads": out[2], "all_kernels_ms": out[3]}
+
+    def set_shard(self, rank, world, allgather):
+        """allgather(send_bytes: bytes) -> bytes of world * len(send_bytes) in rank order (e.g. torch.distributed)."""
+        def _cb(user, send, recv, nbytes):
+            try:
+                data = ctypes.string_at(send, nbytes)
+                out = allgather(data)
+                assert len(out) == nbytes * world
+                ctypes.memmove(recv, out, len(out))
+                return 0
+            except Exception as e:  # noqa: BLE001 - reported through the C error channel
+                self._cb_error = e
+                return 1
+        self._cb = ALLGATHER_FN(_cb) if world > 1 else ctypes.cast(None, ALLGATHER_FN)
+        self._ck(self.lib.zp_prover_set_shard(self.h, rank, world, self._cb, None))
 
     def last_timing(self):
         out = (ctypes.c_double * 5)()
