@@ -1,0 +1,32 @@
+#!/usr/bin/env bash
+# ORACLE — TEST INFRASTRUCTURE ONLY.
+# Compiles the reference's OWN native prover (PNP's C++/CUDA `lib/`, unmodified, taken where it lies under
+# /root/reference — never copied) for sm_100 into oracle/_ref/libzprize_ref.so, following the recipe of
+# "Prize 1B/plonk-core/build.rs":36-103 (blst: gcc -O2 -mno-avx; everything else: nvcc -std=c++17 -O3, here
+# -arch=sm_100 instead of sm_80).  The result exports the reference's `gen_proof` symbol and is used ONLY by
+# tests/test_gpu_vs_pnp_reference.py to cross-run the reference on the GPU box against the oracle and against
+# our library (SURVEY §8c pin (5); valid for Merkle-shaped inputs).
+set -euo pipefail
+cd "$(dirname "$0")"
+REF="${ZP_REFERENCE_ROOT:-/root/reference}/Prize 1B/plonk-core/lib"
+[ -d "$REF" ] || { echo "reference not present; skipping"; exit 0; }
+mkdir -p _ref/pnp_obj
+OUT=_ref/libzprize_ref.so
+[ -f "$OUT" ] && { echo "$OUT exists"; exit 0; }
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+gcc -O2 -mno-avx -fno-builtin -Wno-unused-function -fPIC -D__BLST_PORTABLE__ -I"$REF/blst/include" \
+    -c "$REF/blst/src/server.c" -o _ref/pnp_obj/blst_server.o
+gcc -O2 -fPIC -c "$REF/blst/src/assembly.S" -o _ref/pnp_obj/blst_asm.o
+i=0
+pids=()
+while IFS= read -r -d '' f; do
+  i=$((i+1))
+  o="_ref/pnp_obj/tu_$i.o"
+  ( "$NVCC" -std=c++17 -O3 -arch=sm_100 -Xcompiler -fPIC -ccbin g++ -w -include cstdint -I"$REF/blst/include" -c "$f" -o "$o" ) &
+  pids+=($!)
+  if (( ${#pids[@]} >= ${ZP_JOBS:-8} )); then wait "${pids[0]}"; pids=("${pids[@]:1}"); fi
+done < <(find "$REF/PLONK" "$REF/caffe" "$REF/hello.cu" \( -name '*.cu' -o -name '*.cpp' \) -print0)
+wait || true
+"$NVCC" -shared -arch=sm_100 -o "$OUT" _ref/pnp_obj/*.o -lcudart -lpthread
+rm -rf _ref/pnp_obj
+echo "built $OUT"

@@ -110,7 +110,7 @@ static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = 0) { retur
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
 static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return 0; }
 static inline cudaError_t cudaMemGetInfo(size_t* f, size_t* t) { *f = *t = (size_t)8 << 30; return 0; }
-enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaFuncAttributePreferredSharedMemoryCarveout = 9 };
 template <class F> static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return 0; }
 struct cudaDeviceProp { int multiProcessorCount; char name[64]; int major, minor; size_t totalGlobalMem; };
 static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {

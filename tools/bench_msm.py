@@ -1,0 +1,55 @@
+"""MSM / NTT sweep on the GPU with per-kernel breakdown (device-resident inputs). Results are checked against the
+known-trapdoor identity commit(p) = [p(tau)] G at the smallest size."""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT)
+from conftest import load_package  # noqa: E402
+import oracle_lib  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--logs", default="22")
+    ap.add_argument("--iters", type=int, default=3)
+    ap.add_argument("--ntt", type=int, default=0)
+    args = ap.parse_args()
+    pkg = load_package()
+    lib = pkg.load_library()
+    orc = oracle_lib.load()
+    logs = [int(x) for x in args.logs.split(",")]
+    lmax = max(logs)
+    ctx = pkg.ProverContext(min(lmax, 23), lib)
+    tau = orc.random_fr(7, 1)[0]
+    ctx.generate_srs(tau)
+    n = 1 << min(lmax, 23)
+    ctx.bench_alloc(0, 8 * n if args.ntt else n)
+    if args.ntt:
+        ctx.bench_alloc(1, 8 * n)
+    x = orc.random_fr(2, n)
+    ctx.bench_upload(0, x)
+    for lg in logs:
+        m = 1 << lg
+        ms, out, bd = ctx.bench_msm(0, m, args.iters)
+        line = {"op": "msm", "log_n": lg, "ms": ms, "points_per_s": m / ms * 1e3, "breakdown_ms": bd,
+                "variant": os.environ.get("ZP_ACC_VARIANT", "3")}
+        if lg <= 14:
+            srs = ctx.read_srs(m)
+            line["matches_oracle"] = bool(np.array_equal(out, orc.msm(srs, x[:m].copy())))
+        print(json.dumps(line), flush=True)
+    if args.ntt:
+        for lg in logs + [lmax + 3]:
+            for kind in range(4):
+                ms = ctx.bench_ntt(kind, lg, 0, 1, args.iters)
+                print(json.dumps({"op": "ntt", "kind": kind, "log_n": lg, "ms": ms, "elems_per_s": (1 << lg) / ms * 1e3,
+                                  "algorithmic_GBps": 64.0 * (1 << lg) / ms / 1e6}), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -27,6 +27,7 @@ MsmConfig msm_config_for(size_t n, int c_override) {
     return cfg;
 }
 
+static const int SCAN_TILE_FWD = 2048;
 void MsmWorkspace::reserve(size_t n, const MsmConfig& cfg) {
     size_t wn = (size_t)cfg.nwin * n, wb = (size_t)cfg.nwin * cfg.nbuckets;
     if (digits.n < wn) digits.alloc(wn);
@@ -35,10 +36,22 @@ void MsmWorkspace::reserve(size_t n, const MsmConfig& cfg) {
     if (cursor.n < wb) cursor.alloc(wb);
     if (seg_start.n < wb + 1) seg_start.alloc(wb + 1);
     if (seg_cnt.n < wb) seg_cnt.alloc(wb);
+    if (tile_sum.n < wb / SCAN_TILE_FWD + 2) tile_sum.alloc(wb / SCAN_TILE_FWD + 2);
     size_t mean = (n + cfg.nbuckets - 1) / cfg.nbuckets;
     seg = 2 * mean < 32 ? 32 : 2 * mean;
     max_segs = wn / seg + wb + 1;
     if (segs.n < max_segs) segs.alloc(max_segs);
+    if (desc.n < max_segs) desc.alloc(max_segs);
+    if (!counter.p) counter.alloc(1);
+    if (!sm_count) {
+        int dev = 0;
+        cudaDeviceProp prop;
+        ZP_CUDA(cudaGetDevice(&dev));
+        ZP_CUDA(cudaGetDeviceProperties(&prop, dev));
+        sm_count = prop.multiProcessorCount;
+        const char* v = getenv("ZP_ACC_VARIANT");
+        if (v) acc_variant = atoi(v);
+    }
     size_t np = (size_t)cfg.nwin * MSM_REDUCE_GROUPS;
     if (partial.n < np) partial.alloc(np);
     if (partial_host.size() < np) partial_host.resize(np);
@@ -74,14 +87,32 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(const fr_t* __restrict_
     }
 }
 
-// start[0..m] = exclusive scan of cnt[0..m); cnt[i] <- start[i] (becomes the scatter cursor)
-__global__ void __launch_bounds__(1024) msm_scan_kernel(uint32_t* __restrict__ cnt, uint32_t* __restrict__ start, size_t m) {
+// Exclusive scan of cnt[0..m) in three small launches (tile sums, scan of tile sums, tile-local scan):
+// start[0..m] = exclusive scan; cnt[i] <- start[i] (becomes the scatter cursor).
+static const int SCAN_TILE = 2048;  // elements per CTA (256 threads x 8)
+__global__ void __launch_bounds__(256) msm_scan_tiles_kernel(const uint32_t* __restrict__ cnt, size_t m, uint32_t* __restrict__ tile_sum) {
+    __shared__ uint32_t red[256];
+    size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * 8;
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+        if (base + k < m) s += cnt[base + k];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int d = 128; d >= 1; d >>= 1) {
+        if ((int)threadIdx.x < d) red[threadIdx.x] += red[threadIdx.x + d];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) tile_sum[blockIdx.x] = red[0];
+}
+// single CTA: exclusive scan of up to 1024 * chunk tile sums in place; total written to *total_out
+__global__ void __launch_bounds__(1024) msm_scan_sums_kernel(uint32_t* __restrict__ tile_sum, size_t ntiles, uint32_t* __restrict__ total_out) {
     __shared__ uint32_t part[1024];
     const int t = threadIdx.x;
-    size_t chunk = (m + 1023) / 1024;
-    size_t lo = (size_t)t * chunk, hi = lo + chunk < m ? lo + chunk : m;
+    size_t chunk = (ntiles + 1023) / 1024;
+    size_t lo = (size_t)t * chunk, hi = lo + chunk < ntiles ? lo + chunk : ntiles;
     uint32_t s = 0;
-    for (size_t i = lo; i < hi; i++) s += cnt[i];
+    for (size_t i = lo; i < hi; i++) s += tile_sum[i];
     part[t] = s;
     __syncthreads();
     for (int d = 1; d < 1024; d <<= 1) {
@@ -90,14 +121,47 @@ __global__ void __launch_bounds__(1024) msm_scan_kernel(uint32_t* __restrict__ c
         part[t] += v;
         __syncthreads();
     }
-    uint32_t run = part[t] - s;  // exclusive prefix of this chunk
+    uint32_t run = part[t] - s;
     for (size_t i = lo; i < hi; i++) {
-        uint32_t cval = cnt[i];
-        start[i] = run;
-        cnt[i] = run;
-        run += cval;
+        uint32_t c = tile_sum[i];
+        tile_sum[i] = run;
+        run += c;
     }
-    if (t == 1023) start[m] = part[1023];
+    if (t == 1023) *total_out = part[1023];
+}
+__global__ void __launch_bounds__(256) msm_scan_apply_kernel(uint32_t* __restrict__ cnt, uint32_t* __restrict__ start, size_t m,
+                                                             const uint32_t* __restrict__ tile_sum) {
+    __shared__ uint32_t part[256];
+    size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * 8;
+    uint32_t v[8], s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        v[k] = base + k < m ? cnt[base + k] : 0;
+        s += v[k];
+    }
+    part[threadIdx.x] = s;
+    __syncthreads();
+    for (int d = 1; d < 256; d <<= 1) {
+        uint32_t x = ((int)threadIdx.x >= d) ? part[threadIdx.x - d] : 0;
+        __syncthreads();
+        part[threadIdx.x] += x;
+        __syncthreads();
+    }
+    uint32_t run = tile_sum[blockIdx.x] + part[threadIdx.x] - s;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        if (base + k < m) {
+            start[base + k] = run;
+            cnt[base + k] = run;
+        }
+        run += v[k];
+    }
+}
+static void msm_scan(uint32_t* cnt, uint32_t* start, size_t m, uint32_t* tile_sum, cudaStream_t st) {
+    size_t ntiles = (m + SCAN_TILE - 1) / SCAN_TILE;
+    ZP_LAUNCH(msm_scan_tiles_kernel, dim3((unsigned)ntiles), dim3(256), 0, st, cnt, m, tile_sum);
+    ZP_LAUNCH(msm_scan_sums_kernel, dim3(1), dim3(1024), 0, st, tile_sum, ntiles, start + m);
+    ZP_LAUNCH(msm_scan_apply_kernel, dim3((unsigned)ntiles), dim3(256), 0, st, cnt, start, m, tile_sum);
 }
 
 __global__ void __launch_bounds__(256) msm_scatter_kernel(const uint32_t* __restrict__ digits, size_t n, int nwin, int nbuckets,
@@ -143,37 +207,84 @@ __global__ void __launch_bounds__(256) msm_segcount_kernel(const uint32_t* __res
     seg_cnt[t] = (c + seg - 1) / seg;
 }
 
-// One thread per work segment: XYZZ mixed additions over <= seg points of one bucket.
-__global__ void __launch_bounds__(128) msm_accumulate_kernel(const affine_t* __restrict__ points, const uint32_t* __restrict__ sorted,
-                                                             const uint32_t* __restrict__ start, const uint32_t* __restrict__ endp,
-                                                             const uint32_t* __restrict__ seg_start, size_t nb, uint32_t seg,
-                                                             xyzz_t* __restrict__ segs) {
-    size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= seg_start[nb]) return;
-    // bucket b with seg_start[b] <= s < seg_start[b+1]
-    size_t lo_b = 0, hi_b = nb;
-    while (hi_b - lo_b > 1) {
-        size_t mid = (lo_b + hi_b) >> 1;
-        if (seg_start[mid] <= (uint32_t)s) lo_b = mid; else hi_b = mid;
+// Segment descriptors (first / one-past-last index into `sorted`), one thread per bucket.
+__global__ void __launch_bounds__(256) msm_segdesc_kernel(const uint32_t* __restrict__ start, const uint32_t* __restrict__ endp,
+                                                          const uint32_t* __restrict__ seg_start, size_t nb, uint32_t seg,
+                                                          uint2* __restrict__ desc) {
+    size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    uint32_t s0 = seg_start[b], s1 = seg_start[b + 1], k = start[b], e = endp[b];
+    for (uint32_t s = s0; s < s1; s++) {
+        uint2 d;
+        d.x = k;
+        d.y = k + seg < e ? k + seg : e;
+        desc[s] = d;
+        k += seg;
     }
-    uint32_t k0 = start[lo_b] + ((uint32_t)s - seg_start[lo_b]) * seg;
-    uint32_t k1 = k0 + seg < endp[lo_b] ? k0 + seg : endp[lo_b];
+}
+
+// XYZZ mixed additions over the work segments.  Persistent threads: every lane pulls its next segment
+// from a global counter as soon as it finishes one, so all 32 lanes of a warp keep executing the same
+// point-addition body (no tail divergence from unequal bucket sizes).
+template <int MINBLOCKS>
+__global__ void __launch_bounds__(128, MINBLOCKS) msm_accumulate_kernel(const affine_t* __restrict__ points,
+                                                                        const uint32_t* __restrict__ sorted,
+                                                                        const uint2* __restrict__ desc,
+                                                                        const uint32_t* __restrict__ nseg_ptr,
+                                                                        uint32_t* __restrict__ counter, xyzz_t* __restrict__ segs) {
+    const uint32_t nseg = *nseg_ptr;
+    uint32_t s = atomicAdd(counter, 1u);
+    if (s >= nseg) return;
+    uint2 d = desc[s];
+    uint32_t k = d.x, k1 = d.y;
     xyzz_t acc = xyzz_t::infinity();
-    for (uint32_t k = k0; k < k1; k++) {
+    while (true) {
+        if (k >= k1) {
+            store_xyzz(&segs[s], acc);
+            s = atomicAdd(counter, 1u);
+            if (s >= nseg) break;
+            d = desc[s];
+            k = d.x;
+            k1 = d.y;
+            acc = xyzz_t::infinity();
+        }
         uint32_t e = sorted[k];
         affine_t p = load_affine(&points[e & 0x7fffffffu]);
         if (e >> 31) p.y = p.y.neg();
         acc.add_affine(p.x, p.y);
+        k++;
     }
-    store_xyzz(&segs[s], acc);
+}
+
+// Buckets that were split into several work segments are folded back by one warp each (lanes stride over
+// the segment sums, then a shared-memory tree); afterwards segs[seg_start[b]] holds the whole bucket.
+__global__ void __launch_bounds__(128) msm_fold_kernel(xyzz_t* __restrict__ segs, const uint32_t* __restrict__ seg_start, size_t nb) {
+    __shared__ xyzz_t sm[128];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    size_t b = (size_t)blockIdx.x * 4 + warp;
+    if (b >= nb) return;
+    uint32_t s0 = seg_start[b], s1 = seg_start[b + 1];
+    if (s1 - s0 < 2) return;  // warp-uniform
+    xyzz_t acc = xyzz_t::infinity();
+    for (uint32_t s = s0 + lane; s < s1; s += 32) acc.add(load_xyzz(&segs[s]));
+    xyzz_t* w = sm + warp * 32;
+    w[lane] = acc;
+    __syncwarp();
+    for (int d = 16; d >= 1; d >>= 1) {
+        if (lane < d) {
+            xyzz_t a = w[lane];
+            a.add(w[lane + d]);
+            w[lane] = a;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) store_xyzz(&segs[s0], w[0]);
 }
 
 ZP_D xyzz_t load_bucket(const xyzz_t* __restrict__ segs, const uint32_t* __restrict__ seg_start, size_t b) {
     uint32_t s0 = seg_start[b], s1 = seg_start[b + 1];
     if (s0 == s1) return xyzz_t::infinity();
-    xyzz_t acc = load_xyzz(&segs[s0]);
-    for (uint32_t s = s0 + 1; s < s1; s++) acc.add(load_xyzz(&segs[s]));
-    return acc;
+    return load_xyzz(&segs[s0]);
 }
 
 // One CTA per (window, bucket group).  partial[w * G + g] = sum_{b in group} (b + 1) * bucket[w][b]
@@ -229,7 +340,7 @@ void msm_launch(MsmWorkspace& ws, const MsmConfig& cfg, const affine_t* points, 
                   ws.digits.p, ws.cursor.p);
     }
     mark(1);
-    ZP_LAUNCH(msm_scan_kernel, dim3(1), dim3(1024), 0, st, ws.cursor.p, ws.start.p, wb);
+    msm_scan(ws.cursor.p, ws.start.p, wb, ws.tile_sum.p, st);
     mark(2);
     if (n) {
         ZP_LAUNCH(msm_scatter_kernel, dim3((unsigned)((n + 255) / 256), cfg.nwin), dim3(256), 0, st, ws.digits.p, n, cfg.nwin,
@@ -237,10 +348,27 @@ void msm_launch(MsmWorkspace& ws, const MsmConfig& cfg, const affine_t* points, 
     }
     ZP_LAUNCH(msm_segcount_kernel, dim3((unsigned)((wb + 255) / 256)), dim3(256), 0, st, ws.start.p, ws.cursor.p, wb,
               (uint32_t)ws.seg, ws.seg_cnt.p);
-    ZP_LAUNCH(msm_scan_kernel, dim3(1), dim3(1024), 0, st, ws.seg_cnt.p, ws.seg_start.p, wb);
+    msm_scan(ws.seg_cnt.p, ws.seg_start.p, wb, ws.tile_sum.p, st);
+    ZP_LAUNCH(msm_segdesc_kernel, dim3((unsigned)((wb + 255) / 256)), dim3(256), 0, st, ws.start.p, ws.cursor.p, ws.seg_start.p, wb,
+              (uint32_t)ws.seg, ws.desc.p);
     mark(3);
-    ZP_LAUNCH(msm_accumulate_kernel, dim3((unsigned)((ws.max_segs + 127) / 128)), dim3(128), 0, st, points, ws.sorted.p,
-              ws.start.p, ws.cursor.p, ws.seg_start.p, wb, (uint32_t)ws.seg, ws.segs.p);
+    {
+        ZP_CUDA(cudaMemsetAsync(ws.counter.p, 0, sizeof(uint32_t), st));
+        int variant = ws.acc_variant;
+        int blocks_per_sm = variant == 4 ? 4 : (variant == 5 ? 5 : 3);
+        unsigned grid = (unsigned)(ws.sm_count * blocks_per_sm);
+        if (variant == 4) {
+            auto k = msm_accumulate_kernel<4>;
+            ZP_LAUNCH(k, dim3(grid), dim3(128), 0, st, points, ws.sorted.p, ws.desc.p, ws.seg_start.p + wb, ws.counter.p, ws.segs.p);
+        } else if (variant == 5) {
+            auto k = msm_accumulate_kernel<5>;
+            ZP_LAUNCH(k, dim3(grid), dim3(128), 0, st, points, ws.sorted.p, ws.desc.p, ws.seg_start.p + wb, ws.counter.p, ws.segs.p);
+        } else {
+            auto k = msm_accumulate_kernel<3>;
+            ZP_LAUNCH(k, dim3(grid), dim3(128), 0, st, points, ws.sorted.p, ws.desc.p, ws.seg_start.p + wb, ws.counter.p, ws.segs.p);
+        }
+    }
+    ZP_LAUNCH(msm_fold_kernel, dim3((unsigned)((wb + 3) / 4)), dim3(128), 0, st, ws.segs.p, ws.seg_start.p, wb);
     mark(4);
     int groups = MSM_REDUCE_GROUPS;
     while (cfg.nbuckets / groups < 1) groups >>= 1;

@@ -23,6 +23,11 @@ struct MsmWorkspace {
     DevBuf<uint32_t> seg_start;// [nwin*nbuckets + 1] exclusive scan of ceil(bucket size / seg) (work segments)
     DevBuf<uint32_t> seg_cnt;  // [nwin*nbuckets]
     DevBuf<xyzz_t> segs;       // [<= nwin*n/seg + nwin*nbuckets] partial sum of each work segment
+    DevBuf<uint2> desc;        // [max_segs] (first, last+1) index into `sorted` of each work segment
+    DevBuf<uint32_t> counter;  // dynamic segment counter of the persistent accumulate kernel
+    DevBuf<uint32_t> tile_sum; // scratch of the multi-CTA scan
+    int sm_count = 0;
+    int acc_variant = 3;       // resident CTAs per SM of the accumulate kernel (ZP_ACC_VARIANT=3|4|5)
     size_t seg = 0;            // points per work segment (2x the mean bucket load, >= 32)
     size_t max_segs = 0;
     DevBuf<xyzz_t> partial;    // [nwin * MSM_REDUCE_GROUPS]

@@ -243,6 +243,8 @@ void ntt_run(const NttTables& T, NttScratch& S, NttKind kind, int logn, const fr
         static bool attr_set = false;
         if (!attr_set) {
             ZP_CUDA(cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+            // 64 KiB tiles: ask for the full shared-memory carve-out so that 3 CTAs are resident per SM
+            ZP_CUDA(cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
             attr_set = true;
         }
 #endif
