@@ -120,7 +120,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--height", type=int, default=15)
-    ap.add_argument("--cpu-height", type=int, default=8, dest="cpu_height")
+    ap.add_argument("--cpu-height", type=int, default=10, dest="cpu_height")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -247,6 +247,7 @@ def main():
         step_ms, e2e_step_ms = float(t[0]), float(t[1])
     if rank != 0:
         barrier()
+        dist.destroy_process_group()
         return
 
     # ---- roofline of the dominant kernel (MSM bucket accumulation, integer-pipe bound) + the NTT (HBM)
@@ -305,6 +306,8 @@ def main():
         line["cpu_baseline"] = cpu
     print(json.dumps(line), flush=True)
     barrier()
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -63,3 +63,19 @@ def test_gen_proof_byte_identical_under_emulation(pkg, emu_lib, oracle, n_lookup
     assert oc.verify(proof)[0]
     c.close()
     oc.close()
+
+
+def test_gen_proof_with_precomputed_msm_tables(pkg, emu_lib, oracle, monkeypatch):
+    """Same proof bytes when the commitments go through the precomputed-window MSM tables (forced on for tiny N)."""
+    monkeypatch.setenv("ZP_MSM_PRECOMP_MIN_LOG", "8")
+    oc = oracle_lib.OracleCircuit(oracle, 3, 42, 7, 0)
+    ref_proof, _ = oc.prove()
+    c = pkg.ProverContext(oc.log_n, emu_lib)
+    c.load_srs(oc.srs())
+    c.preprocess(oc.selector_evals(), oc.tables())
+    circ = pkg.make_circuit(oc.cs_n, oc.lookup_len, oc.pi_pos, oc.q_lookup(), oc.pi_canonical(), *oc.wires())
+    assert np.array_equal(c.prove(circ).to_words(), ref_proof)
+    sc = oracle.random_fr(2, oc.n)
+    assert np.array_equal(c.msm(sc), oracle.msm(oc.srs(), sc))
+    c.close()
+    oc.close()

@@ -164,3 +164,14 @@ def test_verifier_key_and_known_tau(pkg, gpu_lib, oracle):
         assert np.array_equal(vk[i], oc.commit_with_tau(co[i]))  # commit(p) == [p(tau)] G
     ctx.close()
     oc.close()
+
+
+def test_precomputed_table_msm_matches_oracle(pkg, gpu_lib, oracle):
+    """MSM over the resident SRS through the precomputed window tables (n >= 2^16) vs the CPU oracle."""
+    ctx = pkg.ProverContext(16, gpu_lib)
+    pts, tau = oracle.srs(7, 1 << 16)
+    ctx.load_srs(pts)
+    sc = oracle.random_fr(2, 1 << 16)
+    sc[:100] = 0
+    assert np.array_equal(ctx.msm(sc), oracle.msm(pts, sc))
+    ctx.close()

@@ -25,25 +25,29 @@ def main():
     orc = oracle_lib.load()
     logs = [int(x) for x in args.logs.split(",")]
     lmax = max(logs)
-    ctx = pkg.ProverContext(min(lmax, 23), lib)
     tau = orc.random_fr(7, 1)[0]
-    ctx.generate_srs(tau)
     n = 1 << min(lmax, 23)
-    ctx.bench_alloc(0, 8 * n if args.ntt else n)
-    if args.ntt:
-        ctx.bench_alloc(1, 8 * n)
     x = orc.random_fr(2, n)
-    ctx.bench_upload(0, x)
     for lg in logs:
+        # one context per size so that window size / precomputed tables are tuned for that size
         m = 1 << lg
-        ms, out, bd = ctx.bench_msm(0, m, args.iters)
+        c = pkg.ProverContext(max(lg, 6), lib)
+        c.generate_srs(tau)
+        c.bench_alloc(0, m)
+        c.bench_upload(0, x[:m].copy())
+        ms, out, bd = c.bench_msm(0, m, args.iters)
+        ctx = c
         line = {"op": "msm", "log_n": lg, "ms": ms, "points_per_s": m / ms * 1e3, "breakdown_ms": bd,
-                "variant": os.environ.get("ZP_ACC_VARIANT", "3")}
+                "precomp": os.environ.get("ZP_MSM_PRECOMP", "1")}
         if lg <= 14:
             srs = ctx.read_srs(m)
             line["matches_oracle"] = bool(np.array_equal(out, orc.msm(srs, x[:m].copy())))
         print(json.dumps(line), flush=True)
     if args.ntt:
+        ctx = pkg.ProverContext(min(lmax, 23), lib)
+        ctx.bench_alloc(0, 8 * n)
+        ctx.bench_alloc(1, 8 * n)
+        ctx.bench_upload(0, x)
         for lg in logs + [lmax + 3]:
             for kind in range(4):
                 ms = ctx.bench_ntt(kind, lg, 0, 1, args.iters)

@@ -222,9 +222,7 @@ int zp_msm_host(zp_prover* p, const uint64_t* scalars, size_t n, uint64_t* out_a
         if (n > pr->srs.n) throw std::runtime_error("zp_msm_host: more scalars than resident SRS points");
         DevBuf<fr_t> s(n);
         ZP_CUDA(cudaMemcpyAsync(s.p, scalars, n * sizeof(fr_t), cudaMemcpyHostToDevice, pr->st));
-        MsmConfig cfg = msm_config_for(n);
-        msm_launch(pr->MW, cfg, pr->srs.p, s.p, n, pr->st);
-        msm_to_affine_out(msm_collect(pr->MW, cfg, pr->st), out_affine);
+        msm_to_affine_out(pr->msm_over_srs(s.p, 0, n, pr->srs.n), out_affine);
     });
 }
 int zp_msm_points_host(zp_prover* p, const uint64_t* points, const uint64_t* scalars, size_t n, int window_bits,
@@ -321,19 +319,13 @@ int zp_bench_msm(zp_prover* p, int slot, size_t n, int iters, double* ms, uint64
         Prover* pr = P(p);
         BenchState& b = bench_of(p);
         if (b.slot[slot].n < n || pr->srs.n < n) throw std::runtime_error("zp_bench_msm: slot or SRS too small");
-        MsmConfig cfg = msm_config_for(n);
         cudaEvent_t e0, e1;
         ZP_CUDA(cudaEventCreate(&e0));
         ZP_CUDA(cudaEventCreate(&e1));
-        host::G1 r = host::G1::infinity();
-        msm_launch(pr->MW, cfg, pr->srs.p, b.slot[slot].p, n, pr->st);  // warm-up (workspace allocation)
-        r = msm_collect(pr->MW, cfg, pr->st);
+        host::G1 r = pr->msm_over_srs(b.slot[slot].p, 0, n, pr->srs.n);  // warm-up (workspace / table allocation)
         pr->MW.timing = true;
         ZP_CUDA(cudaEventRecord(e0, pr->st));
-        for (int i = 0; i < iters; i++) {
-            msm_launch(pr->MW, cfg, pr->srs.p, b.slot[slot].p, n, pr->st);
-            r = msm_collect(pr->MW, cfg, pr->st);
-        }
+        for (int i = 0; i < iters; i++) r = pr->msm_over_srs(b.slot[slot].p, 0, n, pr->srs.n);
         ZP_CUDA(cudaEventRecord(e1, pr->st));
         ZP_CUDA(cudaEventSynchronize(e1));
         float t = 0;

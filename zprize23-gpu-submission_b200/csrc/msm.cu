@@ -24,12 +24,36 @@ MsmConfig msm_config_for(size_t n, int c_override) {
     cfg.c = c;
     cfg.nwin = (256 + c - 1) / c;
     cfg.nbuckets = 1 << (c - 1);
+    cfg.nsets = cfg.nwin;
+    cfg.tab_stride = 0;
+    return cfg;
+}
+
+MsmConfig msm_config_precomp(size_t n, size_t tab_stride) {
+    MsmConfig cfg;
+    int lg = ilog2(n < 2 ? 2 : n);
+    int c = lg - 2;
+    if (c < 12) c = 12;
+    if (c > 20) c = 20;
+    cfg.c = c;
+    cfg.nwin = (256 + c - 1) / c;
+    cfg.nbuckets = 1 << (c - 1);
+    cfg.nsets = 1;
+    cfg.tab_stride = tab_stride;
     return cfg;
 }
 
 static const int SCAN_TILE_FWD = 2048;
+// bucket groups per set for the reduce kernel: at least 128 CTAs in total, at least one bucket per thread
+static int msm_reduce_groups(const MsmConfig& cfg) {
+    int groups = MSM_REDUCE_GROUPS;
+    while (cfg.nsets * groups < 128) groups <<= 1;
+    while (groups > 1 && cfg.nbuckets / groups < 1) groups >>= 1;
+    return groups;
+}
+
 void MsmWorkspace::reserve(size_t n, const MsmConfig& cfg) {
-    size_t wn = (size_t)cfg.nwin * n, wb = (size_t)cfg.nwin * cfg.nbuckets;
+    size_t wn = (size_t)cfg.nwin * n, wb = (size_t)cfg.nsets * cfg.nbuckets;
     if (digits.n < wn) digits.alloc(wn);
     if (sorted.n < wn) sorted.alloc(wn);
     if (start.n < wb + 1) start.alloc(wb + 1);
@@ -37,7 +61,7 @@ void MsmWorkspace::reserve(size_t n, const MsmConfig& cfg) {
     if (seg_start.n < wb + 1) seg_start.alloc(wb + 1);
     if (seg_cnt.n < wb) seg_cnt.alloc(wb);
     if (tile_sum.n < wb / SCAN_TILE_FWD + 2) tile_sum.alloc(wb / SCAN_TILE_FWD + 2);
-    size_t mean = (n + cfg.nbuckets - 1) / cfg.nbuckets;
+    size_t mean = (wn + wb - 1) / wb;  // mean bucket load over all bucket sets
     seg = 2 * mean < 32 ? 32 : 2 * mean;
     max_segs = wn / seg + wb + 1;
     if (segs.n < max_segs) segs.alloc(max_segs);
@@ -52,13 +76,13 @@ void MsmWorkspace::reserve(size_t n, const MsmConfig& cfg) {
         const char* v = getenv("ZP_ACC_VARIANT");
         if (v) acc_variant = atoi(v);
     }
-    size_t np = (size_t)cfg.nwin * MSM_REDUCE_GROUPS;
+    size_t np = (size_t)cfg.nsets * msm_reduce_groups(cfg);
     if (partial.n < np) partial.alloc(np);
     if (partial_host.size() < np) partial_host.resize(np);
 }
 
 __global__ void __launch_bounds__(256) msm_digits_kernel(const fr_t* __restrict__ scalars, size_t n, int c, int nwin, int nbuckets,
-                                                         uint32_t* __restrict__ digits, uint32_t* __restrict__ hist) {
+                                                         int one_set, uint32_t* __restrict__ digits, uint32_t* __restrict__ hist) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     fr_t s = load_fr(&scalars[i]).from_mont();
@@ -83,7 +107,7 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(const fr_t* __restrict_
             carry = 0;
         }
         digits[(size_t)w * n + i] = d | (neg << 31);
-        if (d) atomicAdd(&hist[(size_t)w * nbuckets + d - 1], 1u);
+        if (d) atomicAdd(&hist[(one_set ? 0 : (size_t)w * nbuckets) + d - 1], 1u);
     }
 }
 
@@ -165,15 +189,17 @@ static void msm_scan(uint32_t* cnt, uint32_t* start, size_t m, uint32_t* tile_su
 }
 
 __global__ void __launch_bounds__(256) msm_scatter_kernel(const uint32_t* __restrict__ digits, size_t n, int nwin, int nbuckets,
-                                                          uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted) {
+                                                          size_t tab_stride, uint32_t* __restrict__ cursor,
+                                                          uint32_t* __restrict__ sorted) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     int w = blockIdx.y;
     if (i >= n) return;
     uint32_t dg = digits[(size_t)w * n + i];
     uint32_t d = dg & 0x7fffffffu;
     if (!d) return;
-    uint32_t pos = atomicAdd(&cursor[(size_t)w * nbuckets + d - 1], 1u);
-    sorted[pos] = (uint32_t)i | (dg & 0x80000000u);
+    uint32_t pos = atomicAdd(&cursor[(tab_stride ? 0 : (size_t)w * nbuckets) + d - 1], 1u);
+    // with a precomputed table the entry addresses row w of the table: 2^(c w) * P_i
+    sorted[pos] = (uint32_t)(tab_stride ? (size_t)w * tab_stride + i : i) | (dg & 0x80000000u);
 }
 
 ZP_D affine_t load_affine(const affine_t* p) {
@@ -248,6 +274,8 @@ __global__ void __launch_bounds__(128, MINBLOCKS) msm_accumulate_kernel(const af
             k1 = d.y;
             acc = xyzz_t::infinity();
         }
+        // (software-pipelining the gather one iteration ahead was measured slower: 32.3 vs 30.1 ms — the loop is
+        // multiplier-bound, the extra 24 live registers cost more than the hidden latency)
         uint32_t e = sorted[k];
         affine_t p = load_affine(&points[e & 0x7fffffffu]);
         if (e >> 31) p.y = p.y.neg();
@@ -325,9 +353,32 @@ __global__ void __launch_bounds__(128) msm_reduce_kernel(const xyzz_t* __restric
     if (threadIdx.x == 0) store_xyzz(&partial[blockIdx.x], sm[0]);
 }
 
+// one window row of the precomputed table: dst[i] = 2^c * src[i]  (c doublings in XYZZ, one inversion)
+__global__ void __launch_bounds__(128) msm_table_row_kernel(affine_t* __restrict__ dst, const affine_t* __restrict__ src, size_t n, int c) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    affine_t p = load_affine(&src[i]);
+    xyzz_t a;
+    a.set_double_affine(p.x, p.y);
+    for (int k = 1; k < c; k++) a.dbl_inplace();
+    // the group has prime order, so 2^c * P is finite for finite P
+    fq_t inv = (a.ZZ * a.ZZZ).inverse();
+    fq_t zz_inv = inv * a.ZZZ, zzz_inv = inv * a.ZZ;
+    store_fq(&dst[i].x, a.X * zz_inv);
+    store_fq(&dst[i].y, a.Y * zzz_inv);
+}
+void msm_build_table(affine_t* dst, const affine_t* src, size_t n, int c, int nwin, cudaStream_t st) {
+    ZP_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(affine_t), cudaMemcpyDeviceToDevice, st));
+    for (int w = 1; w < nwin; w++)
+        ZP_LAUNCH(msm_table_row_kernel, dim3((unsigned)((n + 127) / 128)), dim3(128), 0, st, dst + (size_t)w * n,
+                  dst + (size_t)(w - 1) * n, n, c);
+}
+
 void msm_launch(MsmWorkspace& ws, const MsmConfig& cfg, const affine_t* points, const fr_t* scalars, size_t n, cudaStream_t st) {
     ws.reserve(n, cfg);
-    const size_t wb = (size_t)cfg.nwin * cfg.nbuckets;
+    const size_t wb = (size_t)cfg.nsets * cfg.nbuckets;
+    if (cfg.tab_stride && (size_t)cfg.nwin * cfg.tab_stride >= ((size_t)1 << 31))
+        throw std::runtime_error("msm: precomputed table too large for 31-bit indices");
     auto mark = [&](int k) {
         if (!ws.timing) return;
         if (!ws.ev[k]) ZP_CUDA(cudaEventCreate(&ws.ev[k]));
@@ -337,14 +388,14 @@ void msm_launch(MsmWorkspace& ws, const MsmConfig& cfg, const affine_t* points, 
     mark(0);
     if (n) {
         ZP_LAUNCH(msm_digits_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, scalars, n, cfg.c, cfg.nwin, cfg.nbuckets,
-                  ws.digits.p, ws.cursor.p);
+                  cfg.tab_stride ? 1 : 0, ws.digits.p, ws.cursor.p);
     }
     mark(1);
     msm_scan(ws.cursor.p, ws.start.p, wb, ws.tile_sum.p, st);
     mark(2);
     if (n) {
         ZP_LAUNCH(msm_scatter_kernel, dim3((unsigned)((n + 255) / 256), cfg.nwin), dim3(256), 0, st, ws.digits.p, n, cfg.nwin,
-                  cfg.nbuckets, ws.cursor.p, ws.sorted.p);
+                  cfg.nbuckets, cfg.tab_stride, ws.cursor.p, ws.sorted.p);
     }
     ZP_LAUNCH(msm_segcount_kernel, dim3((unsigned)((wb + 255) / 256)), dim3(256), 0, st, ws.start.p, ws.cursor.p, wb,
               (uint32_t)ws.seg, ws.seg_cnt.p);
@@ -370,14 +421,13 @@ void msm_launch(MsmWorkspace& ws, const MsmConfig& cfg, const affine_t* points, 
     }
     ZP_LAUNCH(msm_fold_kernel, dim3((unsigned)((wb + 3) / 4)), dim3(128), 0, st, ws.segs.p, ws.seg_start.p, wb);
     mark(4);
-    int groups = MSM_REDUCE_GROUPS;
-    while (cfg.nbuckets / groups < 1) groups >>= 1;
+    int groups = msm_reduce_groups(cfg);
     int bg = cfg.nbuckets / groups;
     int T = bg < 128 ? bg : 128;
-    ZP_LAUNCH(msm_reduce_kernel, dim3(cfg.nwin * groups), dim3(T), (size_t)T * sizeof(xyzz_t), st, ws.segs.p, ws.seg_start.p,
+    ZP_LAUNCH(msm_reduce_kernel, dim3(cfg.nsets * groups), dim3(T), (size_t)T * sizeof(xyzz_t), st, ws.segs.p, ws.seg_start.p,
               cfg.nbuckets, groups, ws.partial.p);
     mark(5);
-    ZP_CUDA(cudaMemcpyAsync(ws.partial_host.data(), ws.partial.p, (size_t)cfg.nwin * groups * sizeof(xyzz_t),
+    ZP_CUDA(cudaMemcpyAsync(ws.partial_host.data(), ws.partial.p, (size_t)cfg.nsets * groups * sizeof(xyzz_t),
                             cudaMemcpyDeviceToHost, st));
 }
 
@@ -390,12 +440,16 @@ host::G1 msm_collect(MsmWorkspace& ws, const MsmConfig& cfg, cudaStream_t st) {
             ws.last_ms[k] = ms;
         }
     }
-    int groups = MSM_REDUCE_GROUPS;
-    while (cfg.nbuckets / groups < 1) groups >>= 1;
+    int groups = msm_reduce_groups(cfg);
     host::G1 total = host::G1::infinity();
-    for (int w = cfg.nwin - 1; w >= 0; w--) {
-        for (int b = 0; b < cfg.c; b++) total.dbl_inplace();
-        for (int g = 0; g < groups; g++) total.add(host::G1::from_dev(ws.partial_host[(size_t)w * groups + g]));
+    if (cfg.nsets == 1) {
+        // precomputed tables: the window weights are already in the points
+        for (int g = 0; g < groups; g++) total.add(host::G1::from_dev(ws.partial_host[g]));
+    } else {
+        for (int w = cfg.nwin - 1; w >= 0; w--) {
+            for (int b = 0; b < cfg.c; b++) total.dbl_inplace();
+            for (int g = 0; g < groups; g++) total.add(host::G1::from_dev(ws.partial_host[(size_t)w * groups + g]));
+        }
     }
     return total;
 }

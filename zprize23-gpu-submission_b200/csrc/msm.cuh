@@ -9,11 +9,18 @@
 namespace zp {
 
 struct MsmConfig {
-    int c;        // window bits
-    int nwin;     // number of windows = ceil(256 / c)
-    int nbuckets; // per window = 2^(c-1)
+    int c;              // window bits
+    int nwin;           // number of windows = ceil(256 / c)
+    int nbuckets;       // buckets per bucket set = 2^(c-1)
+    int nsets;          // bucket sets: nwin normally, 1 with precomputed window tables
+    size_t tab_stride;  // 0, or the row stride of a precomputed table [w][i] = 2^(c w) * P_i
 };
 MsmConfig msm_config_for(size_t n, int c_override = 0);
+// Precomputed-window variant: with T[w][i] = 2^(c w) P_i resident, every window digit of every scalar goes into ONE
+// bucket set, so c can grow (fewer windows => fewer bucket additions) without multiplying the bucket count.
+MsmConfig msm_config_precomp(size_t n, size_t tab_stride);
+// dst[w * n + i] = 2^(c w) * src[i], w < nwin (dst may be larger than 4 GiB; built once per SRS)
+void msm_build_table(affine_t* dst, const affine_t* src, size_t n, int c, int nwin, cudaStream_t st);
 
 struct MsmWorkspace {
     DevBuf<uint32_t> digits;   // [nwin][n]   |d| | sign << 31

@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(128) quotient_kernel(QuotientArgs a) {
     if (a.sel[7]) arith = arith + g.b.pow5() * load_fr(&a.sel[7][i]);
     if (a.sel[8]) arith = arith + g.d.pow5() * load_fr(&a.sel[8][i]);
     fr_t total = a.sel[9] ? arith * load_fr(&a.sel[9][i]) : fr_t::zero();
-    total = total + load_fr(&a.pi[i]);
+    if (a.pi_count) total = total + a.pi_val * load_fr(&a.l1[(i - a.pi_shift) & (n8 - 1)]);
 
     if (CUSTOM) {
         g.a_next = load_fr(&a.w[0][nx]);

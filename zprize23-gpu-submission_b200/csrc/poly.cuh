@@ -48,7 +48,11 @@ struct QuotientArgs {
     const fr_t* z;            // z coset evaluations
     const fr_t* z2;           // nullptr when the lookup argument is trivial
     const fr_t *f, *table, *h1, *h2;
-    const fr_t* pi;           // public-input polynomial on the coset
+    // public input: PI(X) = pi_val * L_pos(X) and L_pos(x_i) = L_1(x_{i - 8 pos}) on the coset, so the PI stream is a
+    // rotation of the resident l1 array (no NTT, no extra array); pi_count = 0 when the value is zero
+    int pi_count;
+    fr_t pi_val;
+    uint32_t pi_shift;        // 8 * pos
     const fr_t* l1;           // L_1 on the coset (resident, depends on N only)
     const fr_t* sel[15];      // selector coset evaluations in ProverKeyC order; nullptr = identically zero
     const fr_t* sigma[4];

@@ -63,6 +63,10 @@ struct Scope {
 
 // ---- context -----------------------------------------------------------------------------------
 Prover::Prover(int logn_) : logn(logn_), n((size_t)1 << logn_), n8((size_t)8 << logn_) {
+    const char* pc = getenv("ZP_MSM_PRECOMP");
+    if (pc && pc[0] == '0') use_precomp = false;
+    const char* pm = getenv("ZP_MSM_PRECOMP_MIN_LOG");
+    if (pm) precomp_min = (size_t)1 << atoi(pm);
     if (logn < 6 || logn + 3 > NTT_LMAX) throw std::runtime_error("zp_prover_create: log_n must be in [6, 23]");
     ZP_CUDA(cudaStreamCreate(&st));
     T.init(st);
@@ -95,8 +99,6 @@ void Prover::ensure_work_buffers(bool lookup) {
     need(z_poly, n);
     need(z8, n8);
     need(z2_poly, n);
-    need(pi_poly, n);
-    need(pi8, n8);
     need(quot, n8);
     need(t_poly, n8);
     need(num, n);
@@ -113,6 +115,8 @@ void Prover::ensure_work_buffers(bool lookup) {
 }
 
 void Prover::load_srs(const uint64_t* pts, size_t npts) {
+    srs_tab.release();
+    tab_n = 0;
     if (npts < n) throw std::runtime_error("zp_prover_load_srs: fewer than N points");
     srs.alloc(n);  // only the first N powers are ever used (load.cu:348-351)
     ZP_CUDA(cudaMemcpyAsync(srs.p, pts, n * sizeof(affine_t), cudaMemcpyHostToDevice, st));
@@ -157,6 +161,8 @@ static void g1_generator_host(Fq& x, Fq& y) {
 void Prover::generate_srs(const fr_t& tau, size_t npts) {
     if (npts < n) throw std::runtime_error("zp_prover_generate_srs: fewer than N points");
     npts = n;
+    srs_tab.release();
+    tab_n = 0;
     std::vector<affine_t> pow2(255);
     Fq gx, gy;
     g1_generator_host(gx, gy);
@@ -286,6 +292,34 @@ void Prover::finish_pk() {
     have_pk = true;
 }
 
+// sum_{i in [lo, hi)} scalars[i - lo] * srs[i]; large ranges go through the precomputed window table of the
+// slice [lo, lo + slice) (built on first use; 13 x 384 MiB at N = 2^22)
+host::G1 Prover::msm_over_srs(const fr_t* scalars_dev, size_t lo, size_t hi, size_t slice) {
+    MsmConfig cfg = msm_config_for(hi - lo);
+    const affine_t* base = srs.p + lo;
+    if (use_precomp && hi - lo >= precomp_min) {
+        if (!(srs_tab.p && tab_lo == lo && tab_n >= hi - lo)) {
+            if (slice < hi - lo) slice = hi - lo;
+            tab_cfg = msm_config_precomp(slice, slice);
+            srs_tab.alloc((size_t)tab_cfg.nwin * slice);
+            msm_build_table(srs_tab.p, srs.p + lo, slice, tab_cfg.c, tab_cfg.nwin, st);
+            tab_lo = lo;
+            tab_n = slice;
+        }
+        cfg = tab_cfg;
+        base = srs_tab.p;
+    }
+    msm_launch(MW, cfg, base, scalars_dev, hi - lo, st);
+    host::G1 r = msm_collect(MW, cfg, st);
+    if (MW.timing) {
+        msm_acc_ms += MW.last_ms[3];
+        for (int k = 0; k < 5; k++) msm_all_ms += MW.last_ms[k];
+        msm_mads += 10.0 * 588.0 * (double)(hi - lo) * cfg.nwin;  // 10 * 588 * M * W
+        msm_launches++;
+    }
+    return r;
+}
+
 void Prover::commit(const fr_t* coeffs_dev, size_t ncoef, CommitmentC* out, Fq* ox, Fq* oy, bool* oinf) {
     Scope sc(CAT_MSM);
     if (!srs.p) throw std::runtime_error("commit: no SRS loaded");
@@ -298,17 +332,7 @@ void Prover::commit(const fr_t* coeffs_dev, size_t ncoef, CommitmentC* out, Fq* 
         size_t chunk = (ncoef + shard_world - 1) / shard_world;
         size_t lo = std::min(ncoef, (size_t)shard_rank * chunk), hi = std::min(ncoef, lo + chunk);
         host::G1 r = host::G1::infinity();
-        if (hi > lo) {
-            MsmConfig cfg = msm_config_for(hi - lo);
-            msm_launch(MW, cfg, srs.p + lo, coeffs_dev + lo, hi - lo, st);
-            r = msm_collect(MW, cfg, st);
-            if (MW.timing) {
-                msm_acc_ms += MW.last_ms[3];
-                for (int k = 0; k < 5; k++) msm_all_ms += MW.last_ms[k];
-                msm_mads += 10.0 * 588.0 * (double)(hi - lo) * cfg.nwin;  // 10 * 588 * M * W
-                msm_launches++;
-            }
-        }
+        if (hi > lo) r = msm_over_srs(coeffs_dev + lo, lo, hi, std::min(chunk, srs.n - lo));
         if (shard_world > 1) {
             if (!allgather) throw std::runtime_error("commit: sharded prover without an all-gather callback");
             std::vector<host::G1> all(shard_world);
@@ -522,11 +546,7 @@ void Prover::prove_resident(ProofC* out) {
     }
     // z_2 commitment is NOT appended to the transcript (prover.rs:395-397)
 
-    // public-input polynomial (pi.rs:103-116)
-    ZP_CUDA(cudaMemsetAsync(num.p, 0, n * sizeof(fr_t), st));
-    fr_t pi_dev = D(pi_val);
-    if (!pis.empty()) ZP_CUDA(cudaMemcpyAsync(num.p + wit_pi_pos, &pi_dev, sizeof(fr_t), cudaMemcpyHostToDevice, st));
-    { Scope s(CAT_NTT); ntt_run(T, NS, NTT_INV, logn, num.p, n, pi_poly.p, st); }
+    // public-input polynomial (pi.rs:103-116): never materialised — see QuotientArgs::pi_val
 
     // ---- 4. quotient polynomial (prover.rs:402-489, quotient_poly.rs:34-206)
     Fr alpha = tr.challenge_scalar("alpha");
@@ -551,7 +571,6 @@ void Prover::prove_resident(ProofC* out) {
         { Scope s(CAT_NTT);
           for (int k = 0; k < 4; k++) ntt_run(T, NS, NTT_COSET_FWD, logn + 3, w_poly[k].p, n, w8[k].p, st);
           ntt_run(T, NS, NTT_COSET_FWD, logn + 3, z_poly.p, n, z8.p, st);
-          ntt_run(T, NS, NTT_COSET_FWD, logn + 3, pi_poly.p, n, pi8.p, st);
           if (lookup_on) {
               ntt_run(T, NS, NTT_COSET_FWD, logn + 3, z2_poly.p, n, z28.p, st);
               ntt_run(T, NS, NTT_COSET_FWD, logn + 3, f_poly.p, n, f8.p, st);
@@ -565,7 +584,9 @@ void Prover::prove_resident(ProofC* out) {
         qa.z = z8.p;
         qa.z2 = lookup_on ? z28.p : nullptr;
         qa.f = f8.p; qa.table = tb8.p; qa.h1 = h18.p; qa.h2 = h28.p;
-        qa.pi = pi8.p;
+        qa.pi_count = pis.empty() ? 0 : 1;
+        qa.pi_val = D(pi_val);
+        qa.pi_shift = (uint32_t)(8 * wit_pi_pos);
         qa.l1 = l1_coset.p;
         for (int i = 0; i < 15; i++) qa.sel[i] = evals[i].p;
         for (int k = 0; k < 4; k++) qa.sigma[k] = evals[PK_SIGL + k].p;

@@ -32,6 +32,12 @@ struct Prover {
 
     // ---- resident inputs (uploaded / built once, reused by every proof)
     DevBuf<affine_t> srs;
+    // precomputed window table of this rank's SRS slice [tab_lo, tab_lo + tab_n): T[w][i] = 2^(c w) * srs[tab_lo + i]
+    DevBuf<affine_t> srs_tab;
+    size_t tab_lo = 0, tab_n = 0;
+    MsmConfig tab_cfg;
+    bool use_precomp = true;
+    size_t precomp_min = (size_t)1 << 16;  // smallest range that uses the table (ZP_MSM_PRECOMP_MIN_LOG)
     DevBuf<fr_t> coeffs[PK_COUNT];   // N each; empty = identically zero
     DevBuf<fr_t> evals[PK_COUNT];    // 8N each; empty = identically zero
     DevBuf<fr_t> sigma_h[4];         // sigma evaluations on H
@@ -45,7 +51,7 @@ struct Prover {
     DevBuf<fr_t> qlk_ev;
     DevBuf<fr_t> z_poly, z8, z2_poly, z28;
     DevBuf<fr_t> t_ev, f_ev, h1_ev, h2_ev, table_poly, f_poly, h1_poly, h2_poly, tb8, f8, h18, h28;
-    DevBuf<fr_t> pi_poly, pi8, quot, t_poly;
+    DevBuf<fr_t> quot, t_poly;
     DevBuf<fr_t> num, den, lin, comb, wit;
     double last_ms[5] = {0, 0, 0, 0, 0};
     // witness currently resident in w_ev / qlk_ev (set by upload_witness)
@@ -79,6 +85,7 @@ struct Prover {
     void prove_resident(ProofC* out);
     void prove(const CircuitC& c, ProofC* out);
 
+    host::G1 msm_over_srs(const fr_t* scalars_dev, size_t lo, size_t hi, size_t slice);
     // commit to n coefficients (Montgomery) on the device; returns affine point (host)
     void commit(const fr_t* coeffs_dev, size_t ncoef, CommitmentC* out, host::Fq* ox = nullptr, host::Fq* oy = nullptr, bool* oinf = nullptr);
 };
