@@ -170,6 +170,17 @@ def main():
 
         ctx.set_shard(rank, world, allgather)
 
+        class _DevMem:  # wraps prover-owned device memory as a tensor without copying
+            def __init__(self, ptr, nbytes):
+                self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+        def dev_bcast(ptr, nbytes, root):
+            t = torch.as_tensor(_DevMem(ptr, nbytes), device="cuda")
+            dist.broadcast(t, src=root)  # NCCL over NVLink, ordered on the prover's (= torch's current) stream
+
+        if os.environ.get("ZP_DIST_NTT", "1") != "0":
+            ctx.set_device_broadcast(dev_bcast)
+
     # witness in PINNED host memory (what the e2e leg copies from every step)
     def pinned(a):
         t = torch.empty(a.shape, dtype=torch.int64).pin_memory()
@@ -291,7 +302,8 @@ def main():
         "dtype": "u32-limb Montgomery (BLS12-381 Fr/Fq)", "data": "synthetic",
         "config": {"workload": "Poseidon Merkle tree HEIGHT=%d PLONK gen_proof (cs.n=%d, domain 2^%d, zero lookup table), "
                                "witness seed 42, SRS tau seed 7" % (args.height, oc.cs_n, oc.log_n),
-                   "parallelism": "1 proof; MSMs sharded by point range over %d GPU(s), partial sums all-gathered" % world,
+                   "parallelism": "1 proof over %d GPU(s): MSMs sharded by point range (partial sums all-gathered), round-4 coset NTTs dealt "
+                                  "round-robin and quotient pass split by range (NCCL broadcast of finished arrays)" % world,
                    "l2": "inputs larger than L2 (each polynomial 128 MiB, extended arrays 1 GiB)",
                    "resident": "prover key, SRS, twiddles (and the witness for `value`) in HBM before the timed region"},
         "e2e": {"value": e2e_step_ms / 1e3, "unit": "s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},

@@ -160,6 +160,12 @@ int zp_prover_msm_stats(zp_prover* p, double* out4);
  * bytes in rank order; return 0 on success.  world = 1 disables sharding. */
 typedef int (*zp_allgather_fn)(void* user, const void* send, void* recv, size_t bytes_per_rank);
 int zp_prover_set_shard(zp_prover* p, int rank, int world, zp_allgather_fn allgather, void* user);
+/* Optional second hook for the sharded prover: a broadcast of DEVICE memory (`bytes` at `dev_ptr`, from rank `root`
+ * to all ranks, ordered after prior work on the prover's stream — e.g. torch.distributed.broadcast / ncclBroadcast).
+ * When set, the independent 8N coset NTTs of round 4 are computed by different ranks and broadcast over NVLink, and
+ * the fused quotient pass is split by index range (each rank's slice broadcast to the others). */
+typedef int (*zp_dev_broadcast_fn)(void* user, void* dev_ptr, size_t bytes, int root);
+int zp_prover_set_device_broadcast(zp_prover* p, zp_dev_broadcast_fn bcast, void* user);
 /* Device-milliseconds of the phases of the last proof: [0] total, [1] NTT, [2] MSM, [3] quotient,
  * [4] other (CUDA events on the prover's stream). */
 int zp_prover_last_timing(zp_prover* p, double* out_ms, int n);

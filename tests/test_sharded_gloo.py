@@ -44,6 +44,15 @@ def _worker(rank, world, port, emu_path, out_dir):
         return b"".join(bytes(o.numpy()) for o in out)
 
     ctx.set_shard(rank, world, allgather)
+
+    def bcast(ptr, nbytes, root):
+        # under emulation "device" memory is host memory: wrap it without copying and broadcast in place
+        import ctypes
+        buf = (ctypes.c_uint8 * nbytes).from_address(ptr)
+        t = torch.frombuffer(buf, dtype=torch.uint8)
+        dist.broadcast(t, src=root)
+
+    ctx.set_device_broadcast(bcast)
     circ = pkg.make_circuit(oc.cs_n, oc.lookup_len, oc.pi_pos, oc.q_lookup(), oc.pi_canonical(), *oc.wires())
     proof = ctx.prove(circ).to_words()
     np.save(os.path.join(out_dir, "proof_%d.npy" % rank), proof)

@@ -119,6 +119,12 @@ int zp_prover_set_shard(zp_prover* p, int rank, int world, zp_allgather_fn fn, v
         pr->allgather_user = user;
     });
 }
+int zp_prover_set_device_broadcast(zp_prover* p, zp_dev_broadcast_fn fn, void* user) {
+    return guard([&] {
+        P(p)->dev_bcast = fn;
+        P(p)->dev_bcast_user = user;
+    });
+}
 int zp_prover_last_timing(zp_prover* p, double* out_ms, int n) {
     return guard([&] {
         for (int i = 0; i < n && i < 5; i++) out_ms[i] = P(p)->last_ms[i];

@@ -47,8 +47,8 @@ static const int SCAN_TILE_FWD = 2048;
 // bucket groups per set for the reduce kernel: at least 128 CTAs in total, at least one bucket per thread
 static int msm_reduce_groups(const MsmConfig& cfg) {
     int groups = MSM_REDUCE_GROUPS;
-    while (cfg.nsets * groups < 128) groups <<= 1;
-    while (groups > 1 && cfg.nbuckets / groups < 1) groups >>= 1;
+    while (cfg.nsets * groups < 512) groups <<= 1;        // >= 512 CTAs: short per-thread bucket runs
+    while (groups > 1 && cfg.nbuckets / groups < 32) groups >>= 1;  // but at least 32 buckets per CTA
     return groups;
 }
 
@@ -61,12 +61,6 @@ void MsmWorkspace::reserve(size_t n, const MsmConfig& cfg) {
     if (seg_start.n < wb + 1) seg_start.alloc(wb + 1);
     if (seg_cnt.n < wb) seg_cnt.alloc(wb);
     if (tile_sum.n < wb / SCAN_TILE_FWD + 2) tile_sum.alloc(wb / SCAN_TILE_FWD + 2);
-    size_t mean = (wn + wb - 1) / wb;  // mean bucket load over all bucket sets
-    seg = 2 * mean < 32 ? 32 : 2 * mean;
-    max_segs = wn / seg + wb + 1;
-    if (segs.n < max_segs) segs.alloc(max_segs);
-    if (desc.n < max_segs) desc.alloc(max_segs);
-    if (!counter.p) counter.alloc(1);
     if (!sm_count) {
         int dev = 0;
         cudaDeviceProp prop;
@@ -76,8 +70,22 @@ void MsmWorkspace::reserve(size_t n, const MsmConfig& cfg) {
         const char* v = getenv("ZP_ACC_VARIANT");
         if (v) acc_variant = atoi(v);
     }
+    // work-segment length: at most 2x the mean bucket load (so typical buckets are one segment), but short enough
+    // that every persistent thread gets >= 8 segments (load balance on small / sharded inputs), never below 32
+    size_t mean = (wn + wb - 1) / wb;
+    size_t nthreads = (size_t)sm_count * 3 * 128;
+    size_t balanced = wn / (nthreads * 8);
+    seg = 2 * mean;
+    if (balanced < seg) seg = balanced;
+    if (seg < 32) seg = 32;
+    max_segs = wn / seg + wb + 1;
+    if (segs.n < max_segs) segs.alloc(max_segs);
+    if (desc.n < max_segs) desc.alloc(max_segs);
+    if (!counter.p) counter.alloc(1);
     size_t np = (size_t)cfg.nsets * msm_reduce_groups(cfg);
     if (partial.n < np) partial.alloc(np);
+    if (final_sums.n < (size_t)cfg.nsets) final_sums.alloc(cfg.nsets);
+    if (np < (size_t)cfg.nsets) np = cfg.nsets;
     if (partial_host.size() < np) partial_host.resize(np);
 }
 
@@ -374,6 +382,25 @@ void msm_build_table(affine_t* dst, const affine_t* src, size_t n, int c, int nw
                   dst + (size_t)(w - 1) * n, n, c);
 }
 
+// final[set] = sum_g partial[set * groups + g]   (one CTA per bucket set)
+__global__ void __launch_bounds__(128) msm_final_kernel(const xyzz_t* __restrict__ partial, int groups, xyzz_t* __restrict__ final_out) {
+    __shared__ xyzz_t sm[128];
+    const xyzz_t* P = partial + (size_t)blockIdx.x * groups;
+    xyzz_t acc = xyzz_t::infinity();
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) acc.add(load_xyzz(&P[g]));
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for (int d = blockDim.x >> 1; d >= 1; d >>= 1) {
+        if ((int)threadIdx.x < d) {
+            xyzz_t a = sm[threadIdx.x];
+            a.add(sm[threadIdx.x + d]);
+            sm[threadIdx.x] = a;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) store_xyzz(&final_out[blockIdx.x], sm[0]);
+}
+
 void msm_launch(MsmWorkspace& ws, const MsmConfig& cfg, const affine_t* points, const fr_t* scalars, size_t n, cudaStream_t st) {
     ws.reserve(n, cfg);
     const size_t wb = (size_t)cfg.nsets * cfg.nbuckets;
@@ -426,8 +453,9 @@ void msm_launch(MsmWorkspace& ws, const MsmConfig& cfg, const affine_t* points, 
     int T = bg < 128 ? bg : 128;
     ZP_LAUNCH(msm_reduce_kernel, dim3(cfg.nsets * groups), dim3(T), (size_t)T * sizeof(xyzz_t), st, ws.segs.p, ws.seg_start.p,
               cfg.nbuckets, groups, ws.partial.p);
+    ZP_LAUNCH(msm_final_kernel, dim3(cfg.nsets), dim3(128), 0, st, ws.partial.p, groups, ws.final_sums.p);
     mark(5);
-    ZP_CUDA(cudaMemcpyAsync(ws.partial_host.data(), ws.partial.p, (size_t)cfg.nsets * groups * sizeof(xyzz_t),
+    ZP_CUDA(cudaMemcpyAsync(ws.partial_host.data(), ws.final_sums.p, (size_t)cfg.nsets * sizeof(xyzz_t),
                             cudaMemcpyDeviceToHost, st));
 }
 
@@ -440,15 +468,13 @@ host::G1 msm_collect(MsmWorkspace& ws, const MsmConfig& cfg, cudaStream_t st) {
             ws.last_ms[k] = ms;
         }
     }
-    int groups = msm_reduce_groups(cfg);
     host::G1 total = host::G1::infinity();
     if (cfg.nsets == 1) {
-        // precomputed tables: the window weights are already in the points
-        for (int g = 0; g < groups; g++) total.add(host::G1::from_dev(ws.partial_host[g]));
+        total = host::G1::from_dev(ws.partial_host[0]);  // precomputed tables: window weights are in the points
     } else {
         for (int w = cfg.nwin - 1; w >= 0; w--) {
             for (int b = 0; b < cfg.c; b++) total.dbl_inplace();
-            for (int g = 0; g < groups; g++) total.add(host::G1::from_dev(ws.partial_host[(size_t)w * groups + g]));
+            total.add(host::G1::from_dev(ws.partial_host[w]));
         }
     }
     return total;

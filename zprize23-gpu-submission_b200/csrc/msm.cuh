@@ -38,6 +38,7 @@ struct MsmWorkspace {
     size_t seg = 0;            // points per work segment (2x the mean bucket load, >= 32)
     size_t max_segs = 0;
     DevBuf<xyzz_t> partial;    // [nwin * MSM_REDUCE_GROUPS]
+    DevBuf<xyzz_t> final_sums; // [nsets] per-set sums (what returns to the host)
     std::vector<xyzz_t> partial_host;
     // optional per-kernel timing (bench only): digits, scan, scatter, accumulate, reduce
     bool timing = false;

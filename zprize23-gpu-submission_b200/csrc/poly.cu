@@ -392,7 +392,8 @@ template <bool CUSTOM, bool LOOKUP>
 __global__ void __launch_bounds__(128) quotient_kernel(QuotientArgs a) {
     const size_t n8 = (size_t)1 << (a.logn + 3);
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n8) return;
+    if (i >= a.i_count) return;
+    i += a.i_begin;
     size_t nx = (i + 8) & (n8 - 1);
     const fr_t one = fr_t::one();
     GateVals<fr_t> g;
@@ -466,7 +467,8 @@ void quotient_evals(const QuotientArgs& a, cudaStream_t st) {
     size_t n8 = (size_t)1 << (a.logn + 3);
     bool custom = a.sel[10] || a.sel[11] || a.sel[12] || a.sel[13];
     bool lookup = a.z2 != nullptr;
-    dim3 grid((unsigned)((n8 + 127) / 128)), block(128);
+    (void)n8;
+    dim3 grid((unsigned)((a.i_count + 127) / 128)), block(128);
     if (custom && lookup) {
         auto k = quotient_kernel<true, true>;
         ZP_LAUNCH(k, grid, block, 0, st, a);

@@ -62,6 +62,7 @@ struct QuotientArgs {
     const fr_t *w_lo, *w_hi;  // omega tables (for x = g * omega_8N^i)
     fr_t g;                   // coset generator 7
     fr_t* out;
+    size_t i_begin, i_count;  // index range of the coset handled by this launch (whole coset: 0, 8N)
 };
 void quotient_evals(const QuotientArgs& a, cudaStream_t st);
 

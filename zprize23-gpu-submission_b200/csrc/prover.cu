@@ -568,16 +568,28 @@ void Prover::prove_resident(ProofC* out) {
     Fr coeff_d;
     memcpy(coeff_d.v, JUBJUB_D, 32);
     {
+        // the 8N coset NTTs of this round are independent: with a device broadcast hook they are dealt round-robin
+        // to the ranks and the finished 1 GiB arrays are exchanged over NVLink; otherwise every rank computes all
+        const bool dist = shard_world > 1 && dev_bcast != nullptr && (n8 % (size_t)shard_world) == 0;
+        struct Job { const fr_t* in; fr_t* out; };
+        std::vector<Job> jobs;
+        for (int k = 0; k < 4; k++) jobs.push_back({w_poly[k].p, w8[k].p});
+        jobs.push_back({z_poly.p, z8.p});
+        if (lookup_on) {
+            jobs.push_back({z2_poly.p, z28.p});
+            jobs.push_back({f_poly.p, f8.p});
+            jobs.push_back({table_poly.p, tb8.p});
+            jobs.push_back({h1_poly.p, h18.p});
+            jobs.push_back({h2_poly.p, h28.p});
+        }
         { Scope s(CAT_NTT);
-          for (int k = 0; k < 4; k++) ntt_run(T, NS, NTT_COSET_FWD, logn + 3, w_poly[k].p, n, w8[k].p, st);
-          ntt_run(T, NS, NTT_COSET_FWD, logn + 3, z_poly.p, n, z8.p, st);
-          if (lookup_on) {
-              ntt_run(T, NS, NTT_COSET_FWD, logn + 3, z2_poly.p, n, z28.p, st);
-              ntt_run(T, NS, NTT_COSET_FWD, logn + 3, f_poly.p, n, f8.p, st);
-              ntt_run(T, NS, NTT_COSET_FWD, logn + 3, table_poly.p, n, tb8.p, st);
-              ntt_run(T, NS, NTT_COSET_FWD, logn + 3, h1_poly.p, n, h18.p, st);
-              ntt_run(T, NS, NTT_COSET_FWD, logn + 3, h2_poly.p, n, h28.p, st);
-          } }
+          for (size_t k = 0; k < jobs.size(); k++)
+              if (!dist || (int)(k % shard_world) == shard_rank) ntt_run(T, NS, NTT_COSET_FWD, logn + 3, jobs[k].in, n, jobs[k].out, st);
+          if (dist)
+              for (size_t k = 0; k < jobs.size(); k++)
+                  if (dev_bcast(dev_bcast_user, jobs[k].out, n8 * sizeof(fr_t), (int)(k % shard_world)) != 0)
+                      throw std::runtime_error("device broadcast of a coset NTT failed");
+        }
         QuotientArgs qa;
         qa.logn = logn;
         for (int k = 0; k < 4; k++) qa.w[k] = w8[k].p;
@@ -605,7 +617,19 @@ void Prover::prove_resident(ProofC* out) {
         qa.w_hi = T.w_hi.p;
         qa.g = fr_generator_host();
         qa.out = quot.p;
-        { Scope s(CAT_QUOT); quotient_evals(qa, st); }
+        qa.i_begin = 0;
+        qa.i_count = n8;
+        if (dist) {  // each rank evaluates its slice of the coset, slices are broadcast to everybody
+            qa.i_count = n8 / shard_world;
+            qa.i_begin = qa.i_count * shard_rank;
+        }
+        { Scope s(CAT_QUOT);
+          quotient_evals(qa, st);
+          if (dist)
+              for (int r = 0; r < shard_world; r++)
+                  if (dev_bcast(dev_bcast_user, quot.p + (size_t)r * qa.i_count, qa.i_count * sizeof(fr_t), r) != 0)
+                      throw std::runtime_error("device broadcast of a quotient slice failed");
+        }
         { Scope s(CAT_NTT); ntt_run(T, NS, NTT_COSET_INV, logn + 3, quot.p, n8, t_poly.p, st); }
     }
     static const char* tl[8] = {"t_1", "t_2", "t_3", "t_4", "t_5", "t_6", "t_7", "t_8"};

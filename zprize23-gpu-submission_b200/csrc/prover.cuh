@@ -70,6 +70,8 @@ struct Prover {
     int shard_rank = 0, shard_world = 1;
     zp_allgather_fn allgather = nullptr;
     void* allgather_user = nullptr;
+    zp_dev_broadcast_fn dev_bcast = nullptr;
+    void* dev_bcast_user = nullptr;
 
     explicit Prover(int logn_);
     ~Prover();

@@ -102,6 +102,10 @@ assert ctypes.sizeof(ProofC) == 2656 and ctypes.sizeof(ProverKeyC) == 44 * 8 and
 ALLGATHER_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t)
 
 
+# int (*zp_dev_broadcast_fn)(void* user, void* dev_ptr, size_t bytes, int root)
+DEV_BCAST_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int)
+
+
 class ZprizeError(RuntimeError):
     pass
 
@@ -144,6 +148,7 @@ def load_library(path=None):
         "zp_prover_collect_msm_stats": (ci, [vp, ci]),
         "zp_prover_msm_stats": (ci, [vp, dp]),
         "zp_prover_set_shard": (ci, [vp, ci, ci, ALLGATHER_FN, vp]),
+        "zp_prover_set_device_broadcast": (ci, [vp, DEV_BCAST_FN, vp]),
         "zp_ntt_host": (ci, [vp, ci, ci, u64p, u64p]),
         "zp_msm_host": (ci, [vp, u64p, cs, u64p]),
         "zp_msm_points_host": (ci, [vp, u64p, u64p, cs, ci, u64p]),
@@ -171,7 +176,7 @@ EXPORTED_SYMBOLS = ["gen_proof", "zp_last_error", "zp_launch_count", "zp_device_
                     "zp_prover_destroy", "zp_prover_set_label", "zp_profiler_range", "zp_prover_set_stream", "zp_prover_load_srs", "zp_prover_generate_srs",
                     "zp_prover_read_srs", "zp_prover_load_pk", "zp_prover_preprocess", "zp_prover_verifier_key",
                     "zp_prover_prove", "zp_prover_last_timing", "zp_prover_upload_witness", "zp_prover_prove_resident",
-                    "zp_prover_collect_msm_stats", "zp_prover_msm_stats", "zp_prover_set_shard", "zp_ntt_host", "zp_msm_host", "zp_msm_points_host",
+                    "zp_prover_collect_msm_stats", "zp_prover_msm_stats", "zp_prover_set_shard", "zp_prover_set_device_broadcast", "zp_ntt_host", "zp_msm_host", "zp_msm_points_host",
                     "zp_poly_eval_host", "zp_poly_divide_host", "zp_prefix_product_host", "zp_bench_alloc",
                     "zp_bench_upload", "zp_bench_download", "zp_bench_ntt", "zp_bench_msm", "zp_bench_msm_breakdown",
                     "zp_bench_int_pipe"]
@@ -313,6 +318,21 @@ class ProverContext:
                 return 1
         self._cb = ALLGATHER_FN(_cb) if world > 1 else ctypes.cast(None, ALLGATHER_FN)
         self._ck(self.lib.zp_prover_set_shard(self.h, rank, world, self._cb, None))
+
+    def set_device_broadcast(self, bcast):
+        """bcast(dev_ptr: int, nbytes: int, root: int) broadcasts device memory in place (None disables)."""
+        if bcast is None:
+            self._bc = ctypes.cast(None, DEV_BCAST_FN)
+        else:
+            def _cb(user, ptr, nbytes, root):
+                try:
+                    bcast(ptr, nbytes, root)
+                    return 0
+                except Exception as e:  # noqa: BLE001
+                    self._cb_error = e
+                    return 1
+            self._bc = DEV_BCAST_FN(_cb)
+        self._ck(self.lib.zp_prover_set_device_broadcast(self.h, self._bc, None))
 
     def last_timing(self):
         out = (ctypes.c_double * 5)()
