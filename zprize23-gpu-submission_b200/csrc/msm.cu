@@ -47,8 +47,9 @@ static const int SCAN_TILE_FWD = 2048;
 // bucket groups per set for the reduce kernel: at least 128 CTAs in total, at least one bucket per thread
 static int msm_reduce_groups(const MsmConfig& cfg) {
     int groups = MSM_REDUCE_GROUPS;
-    while (cfg.nsets * groups < 512) groups <<= 1;        // >= 512 CTAs: short per-thread bucket runs
-    while (groups > 1 && cfg.nbuckets / groups < 32) groups >>= 1;  // but at least 32 buckets per CTA
+    while (cfg.nsets * groups < 128) groups <<= 1;  // >= 128 CTAs (512 was measured slower: the per-thread scalar
+                                                    // multiplication by the bucket offset then dominates)
+    while (groups > 1 && cfg.nbuckets / groups < 1) groups >>= 1;
     return groups;
 }
 
@@ -292,6 +293,19 @@ __global__ void __launch_bounds__(128, MINBLOCKS) msm_accumulate_kernel(const af
     }
 }
 
+// Buckets split into a few work segments (the common case on small / sharded inputs) are folded by one THREAD each
+// (all lanes busy); long runs (skewed digit distributions) by one warp each in msm_fold_kernel.
+static const uint32_t FOLD_SERIAL_MAX = 8;
+__global__ void __launch_bounds__(128) msm_fold_small_kernel(xyzz_t* __restrict__ segs, const uint32_t* __restrict__ seg_start, size_t nb) {
+    size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    uint32_t s0 = seg_start[b], s1 = seg_start[b + 1];
+    if (s1 - s0 < 2 || s1 - s0 > FOLD_SERIAL_MAX) return;
+    xyzz_t acc = load_xyzz(&segs[s0]);
+    for (uint32_t s = s0 + 1; s < s1; s++) acc.add(load_xyzz(&segs[s]));
+    store_xyzz(&segs[s0], acc);
+}
+
 // Buckets that were split into several work segments are folded back by one warp each (lanes stride over
 // the segment sums, then a shared-memory tree); afterwards segs[seg_start[b]] holds the whole bucket.
 __global__ void __launch_bounds__(128) msm_fold_kernel(xyzz_t* __restrict__ segs, const uint32_t* __restrict__ seg_start, size_t nb) {
@@ -300,7 +314,7 @@ __global__ void __launch_bounds__(128) msm_fold_kernel(xyzz_t* __restrict__ segs
     size_t b = (size_t)blockIdx.x * 4 + warp;
     if (b >= nb) return;
     uint32_t s0 = seg_start[b], s1 = seg_start[b + 1];
-    if (s1 - s0 < 2) return;  // warp-uniform
+    if (s1 - s0 <= FOLD_SERIAL_MAX) return;  // warp-uniform; short runs were folded by msm_fold_small_kernel
     xyzz_t acc = xyzz_t::infinity();
     for (uint32_t s = s0 + lane; s < s1; s += 32) acc.add(load_xyzz(&segs[s]));
     xyzz_t* w = sm + warp * 32;
@@ -446,6 +460,7 @@ void msm_launch(MsmWorkspace& ws, const MsmConfig& cfg, const affine_t* points, 
             ZP_LAUNCH(k, dim3(grid), dim3(128), 0, st, points, ws.sorted.p, ws.desc.p, ws.seg_start.p + wb, ws.counter.p, ws.segs.p);
         }
     }
+    ZP_LAUNCH(msm_fold_small_kernel, dim3((unsigned)((wb + 127) / 128)), dim3(128), 0, st, ws.segs.p, ws.seg_start.p, wb);
     ZP_LAUNCH(msm_fold_kernel, dim3((unsigned)((wb + 3) / 4)), dim3(128), 0, st, ws.segs.p, ws.seg_start.p, wb);
     mark(4);
     int groups = msm_reduce_groups(cfg);
