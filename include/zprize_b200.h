@@ -173,6 +173,15 @@ int zp_prover_last_timing(zp_prover* p, double* out_ms, int n);
 /* ---- operator entry points for the sweeps (function.cuh:45-113 equivalents) ------------------ */
 /* kind: 0 NTT, 1 iNTT, 2 coset-NTT (g = 7), 3 coset-iNTT; natural order in/out; host buffers. */
 int zp_ntt_host(zp_prover* p, int kind, int log_n, const uint64_t* in, uint64_t* out);
+/* Four-step NTT sharded over `world` (1, 2, 4, 8) ranks, one process per GPU: `local_in` / `local_out` are this rank's
+ * contiguous blocks [rank*N/world, (rank+1)*N/world) of the natural-order input / output (host memory), N = 2^log_n;
+ * `alltoall(user, send_dev, recv_dev, bytes_per_peer)` exchanges DEVICE memory (chunk p of send -> rank p). */
+typedef int (*zp_dev_alltoall_fn)(void* user, const void* send_dev, void* recv_dev, size_t bytes_per_peer);
+int zp_ntt_sharded_host(zp_prover* p, int kind, int log_n, int rank, int world, const uint64_t* local_in, uint64_t* local_out,
+                        zp_dev_alltoall_fn alltoall, void* user);
+/* device-resident timing variant: block in slot_in, result in slot_out, two more slots as scratch; *ms = average */
+int zp_bench_ntt_sharded(zp_prover* p, int kind, int log_n, int rank, int world, int slot_in, int slot_out, int slot_tmp_a,
+                         int slot_tmp_b, int iters, zp_dev_alltoall_fn alltoall, void* user, double* ms);
 /* MSM over the first n points of the resident SRS with n host scalars (Montgomery Fr). out: affine. */
 int zp_msm_host(zp_prover* p, const uint64_t* scalars, size_t n, uint64_t* out_affine);
 /* MSM with caller-supplied points (n * 12 u64, host). window_bits = 0 picks the default. */

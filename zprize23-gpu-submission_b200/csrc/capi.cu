@@ -215,6 +215,42 @@ int zp_ntt_host(zp_prover* p, int kind, int log_n, const uint64_t* in, uint64_t*
         ZP_CUDA(cudaStreamSynchronize(pr->st));
     });
 }
+int zp_ntt_sharded_host(zp_prover* p, int kind, int log_n, int rank, int world, const uint64_t* in, uint64_t* out,
+                        zp_dev_alltoall_fn a2a, void* user) {
+    return guard([&] {
+        Prover* pr = P(p);
+        size_t M = ((size_t)1 << log_n) / world;
+        DevBuf<fr_t> a(M), b(M), ta(M), tb(M);
+        ZP_CUDA(cudaMemcpyAsync(a.p, in, M * sizeof(fr_t), cudaMemcpyHostToDevice, pr->st));
+        ntt_sharded_run(pr->T, pr->NS, (NttKind)kind, log_n, rank, world, a.p, b.p, ta.p, tb.p, a2a, user, pr->st);
+        ZP_CUDA(cudaMemcpyAsync(out, b.p, M * sizeof(fr_t), cudaMemcpyDeviceToHost, pr->st));
+        ZP_CUDA(cudaStreamSynchronize(pr->st));
+    });
+}
+int zp_bench_ntt_sharded(zp_prover* p, int kind, int log_n, int rank, int world, int slot_in, int slot_out, int slot_ta, int slot_tb,
+                         int iters, zp_dev_alltoall_fn a2a, void* user, double* ms) {
+    return guard([&] {
+        Prover* pr = P(p);
+        BenchState& b = bench_of(p);
+        size_t M = ((size_t)1 << log_n) / world;
+        for (int s : {slot_in, slot_out, slot_ta, slot_tb})
+            if (s < 0 || s >= 8 || b.slot[s].n < M) throw std::runtime_error("zp_bench_ntt_sharded: slots too small");
+        cudaEvent_t e0, e1;
+        ZP_CUDA(cudaEventCreate(&e0));
+        ZP_CUDA(cudaEventCreate(&e1));
+        ZP_CUDA(cudaEventRecord(e0, pr->st));
+        for (int i = 0; i < iters; i++)
+            ntt_sharded_run(pr->T, pr->NS, (NttKind)kind, log_n, rank, world, b.slot[slot_in].p, b.slot[slot_out].p, b.slot[slot_ta].p,
+                            b.slot[slot_tb].p, a2a, user, pr->st);
+        ZP_CUDA(cudaEventRecord(e1, pr->st));
+        ZP_CUDA(cudaEventSynchronize(e1));
+        float t = 0;
+        ZP_CUDA(cudaEventElapsedTime(&t, e0, e1));
+        *ms = t / iters;
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    });
+}
 static void msm_to_affine_out(const host::G1& r, uint64_t* out) {
     host::Fq x, y;
     bool inf;

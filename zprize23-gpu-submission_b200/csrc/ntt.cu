@@ -256,3 +256,119 @@ void ntt_run(const NttTables& T, NttScratch& S, NttKind kind, int logn, const fr
 }
 
 }  // namespace zp
+
+// =====================================================================================================
+// Four-step NTT over G ranks.  N = G*M, m = M/G.  With n = n2*G + n1 and k = k1*M + k2:
+//     X[k1*M + k2] = sum_{n1} w_G^{n1 k1} * ( w_N^{n1 k2} * sum_{n2} w_M^{n2 k2} x[n2*G + n1] )
+// so a rank that holds the CYCLIC slice n1 = r runs one local size-M transform, multiplies by w_N^{r k2},
+// exchanges k2-ranges (all-to-all) and finishes with size-G butterflies.  Two more all-to-alls convert the
+// caller's contiguous blocks to the cyclic slice and the block-cyclic result back to contiguous blocks; at
+// NVLink bandwidth each moves (G-1)/G * 32*M bytes per GPU (0.2 ms at N = 2^25, G = 8).
+// =====================================================================================================
+namespace zp {
+
+// send[p][i] = in[i*G + p] * (coset ? g^(r*M + i*G + p) : 1)        (block -> cyclic redistribution, packed per peer)
+__global__ void ntt4_pack_kernel(const fr_t* __restrict__ in, fr_t* __restrict__ send, size_t M, int lg, size_t base, int coset,
+                                 const fr_t* c_lo, const fr_t* c_hi) {
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= M) return;
+    size_t G = (size_t)1 << lg, m = M >> lg;
+    fr_t v = load_fr(&in[j]);
+    if (coset) {
+        size_t n = base + j;
+        uint32_t lo = (uint32_t)n & ((1u << NTT_LO_BITS) - 1), hi = (uint32_t)(n >> NTT_LO_BITS);
+        if (lo) v = v * load_fr(&c_lo[lo]);
+        if (hi) v = v * load_fr(&c_hi[hi]);
+    }
+    size_t p = j & (G - 1), i = j >> lg;
+    store_fr(&send[p * m + i], v);
+}
+// y[k2] *= w_N^{+-(r * k2)}
+__global__ void ntt4_twiddle_kernel(fr_t* __restrict__ y, size_t M, int logn_total, int rank, int inverse, const fr_t* w_lo,
+                                    const fr_t* w_hi) {
+    size_t k2 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k2 >= M || rank == 0) return;
+    uint64_t e = ((uint64_t)rank * k2) & (((uint64_t)1 << logn_total) - 1);
+    uint32_t ex = (uint32_t)(e << (NTT_LMAX - logn_total));
+    if (!ex) return;
+    if (inverse) ex = ((1u << NTT_LMAX) - ex) & ((1u << NTT_LMAX) - 1);
+    store_fr(&y[k2], load_fr(&y[k2]) * tw_lookup(w_lo, w_hi, ex));
+}
+// out[k1][i] = scale * sum_{n1} w_G^{+-(n1 k1)} in[n1][i], G <= 8, radix-2 DIF in registers
+__global__ void ntt4_butterfly_kernel(const fr_t* __restrict__ in, fr_t* __restrict__ out, size_t m, int lg, int inverse, int do_scale,
+                                      fr_t scale, const fr_t* w_lo, const fr_t* w_hi) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const int G = 1 << lg;
+    fr_t v[8];
+    for (int a = 0; a < G; a++) v[a] = load_fr(&in[(size_t)a * m + i]);
+    for (int s = 0; s < lg; s++) {
+        int half = G >> (s + 1);
+        for (int t = 0; t < G / 2; t++) {
+            int j = t & (half - 1), blk = t / half;
+            int i0 = blk * 2 * half + j, i1 = i0 + half;
+            fr_t u = v[i0], w = v[i1];
+            v[i0] = u + w;
+            fr_t d = u - w;
+            if (j) {
+                uint32_t ex = ((uint32_t)j << s) << (NTT_LMAX - lg);
+                if (inverse) ex = ((1u << NTT_LMAX) - ex) & ((1u << NTT_LMAX) - 1);
+                d = d * tw_lookup(w_lo, w_hi, ex);
+            }
+            v[i1] = d;
+        }
+    }
+    for (int k1 = 0; k1 < G; k1++) {
+        int row = lg ? (int)(__brev((uint32_t)k1) >> (32 - lg)) : 0;
+        fr_t r = v[row];
+        if (do_scale) r = r * scale;
+        store_fr(&out[(size_t)k1 * m + i], r);
+    }
+}
+// out[j] = in[j] * g^-(base + j) (coset inverse post-scaling; 1/N already applied)
+__global__ void ntt4_coset_out_kernel(fr_t* __restrict__ data, size_t M, size_t base, const fr_t* c_lo, const fr_t* c_hi) {
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= M) return;
+    size_t n = base + j;
+    uint32_t lo = (uint32_t)n & ((1u << NTT_LO_BITS) - 1), hi = (uint32_t)(n >> NTT_LO_BITS);
+    fr_t v = load_fr(&data[j]);
+    if (lo) v = v * load_fr(&c_lo[lo]);
+    if (hi) v = v * load_fr(&c_hi[hi]);
+    store_fr(&data[j], v);
+}
+
+void ntt_sharded_run(const NttTables& T, NttScratch& S, NttKind kind, int logn_total, int rank, int world, const fr_t* in_local,
+                     fr_t* out_local, fr_t* tmp_a, fr_t* tmp_b, ntt_alltoall_fn a2a, void* user, cudaStream_t st) {
+    int lg = ilog2((size_t)world);
+    if (((size_t)1 << lg) != (size_t)world || world > 8) throw std::runtime_error("ntt_sharded_run: world must be 1, 2, 4 or 8");
+    if (logn_total > NTT_LMAX || logn_total < 2 * lg) throw std::runtime_error("ntt_sharded_run: unsupported size");
+    const bool inverse = (kind == NTT_INV || kind == NTT_COSET_INV);
+    if (world == 1) {
+        ntt_run(T, S, kind, logn_total, in_local, (size_t)1 << logn_total, out_local, st);
+        return;
+    }
+    const size_t M = (size_t)1 << (logn_total - lg), m = M >> lg;
+    const size_t peer_bytes = m * sizeof(fr_t);
+    const unsigned gM = (unsigned)((M + 255) / 256), gm = (unsigned)((m + 255) / 256);
+    auto exchange = [&](const fr_t* send, fr_t* recv) {
+        if (a2a(user, send, recv, peer_bytes) != 0) throw std::runtime_error("ntt_sharded_run: all-to-all failed");
+    };
+    // 1. block -> cyclic (coset-forward powers g^n folded into the pack)
+    ZP_LAUNCH(ntt4_pack_kernel, dim3(gM), dim3(256), 0, st, in_local, tmp_a, M, lg, (size_t)rank * M, kind == NTT_COSET_FWD ? 1 : 0,
+              T.g_lo.p, T.g_hi.p);
+    exchange(tmp_a, tmp_b);
+    // 2. local size-M transform of the cyclic slice (the 1/M of the inverse comes with it)
+    ntt_run(T, S, inverse ? NTT_INV : NTT_FWD, logn_total - lg, tmp_b, M, tmp_a, st);
+    // 3. twiddle w_N^{r k2}
+    ZP_LAUNCH(ntt4_twiddle_kernel, dim3(gM), dim3(256), 0, st, tmp_a, M, logn_total, rank, inverse ? 1 : 0, T.w_lo.p, T.w_hi.p);
+    // 4. exchange k2 ranges, 5. size-G butterflies over n1 (times 1/G for the inverse)
+    exchange(tmp_a, tmp_b);
+    ZP_LAUNCH(ntt4_butterfly_kernel, dim3(gm), dim3(256), 0, st, tmp_b, tmp_a, m, lg, inverse ? 1 : 0, inverse ? 1 : 0, T.ninv[lg],
+              T.w_lo.p, T.w_hi.p);
+    // 6. block-cyclic -> contiguous blocks
+    exchange(tmp_a, out_local);
+    if (kind == NTT_COSET_INV)
+        ZP_LAUNCH(ntt4_coset_out_kernel, dim3(gM), dim3(256), 0, st, out_local, M, (size_t)rank * M, T.gi_lo.p, T.gi_hi.p);
+}
+
+}  // namespace zp

@@ -43,3 +43,13 @@ fr_t fr_two_adic_root_host();
 fr_t fr_generator_host();
 
 }  // namespace zp
+
+// ---- four-step NTT sharded over G ranks (one process per GPU) -----------------------------------
+// Rank r holds the contiguous block x[r*M, (r+1)*M), M = N/G, and ends with the contiguous block X[r*M, (r+1)*M) of
+// the transform (natural order, same semantics as ntt_run).  `alltoall(user, send, recv, bytes_per_peer)` exchanges
+// device memory: chunk p of `send` goes to rank p, chunk q of `recv` comes from rank q (NCCL all-to-all over NVLink).
+namespace zp {
+typedef int (*ntt_alltoall_fn)(void* user, const void* send_dev, void* recv_dev, size_t bytes_per_peer);
+void ntt_sharded_run(const NttTables& T, NttScratch& S, NttKind kind, int logn_total, int rank, int world, const fr_t* in_local,
+                     fr_t* out_local, fr_t* tmp_a, fr_t* tmp_b, ntt_alltoall_fn a2a, void* user, cudaStream_t st);
+}  // namespace zp

@@ -106,6 +106,10 @@ ALLGATHER_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, 
 DEV_BCAST_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int)
 
 
+# int (*zp_dev_alltoall_fn)(void* user, const void* send_dev, void* recv_dev, size_t bytes_per_peer)
+DEV_A2A_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t)
+
+
 class ZprizeError(RuntimeError):
     pass
 
@@ -151,6 +155,8 @@ def load_library(path=None):
         "zp_prover_set_device_broadcast": (ci, [vp, DEV_BCAST_FN, vp]),
         "zp_ntt_host": (ci, [vp, ci, ci, u64p, u64p]),
         "zp_msm_host": (ci, [vp, u64p, cs, u64p]),
+        "zp_ntt_sharded_host": (ci, [vp, ci, ci, ci, ci, u64p, u64p, DEV_A2A_FN, vp]),
+        "zp_bench_ntt_sharded": (ci, [vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, DEV_A2A_FN, vp, dp]),
         "zp_msm_points_host": (ci, [vp, u64p, u64p, cs, ci, u64p]),
         "zp_poly_eval_host": (ci, [vp, u64p, cs, u64p, u64p]),
         "zp_poly_divide_host": (ci, [vp, u64p, cs, u64p, u64p]),
@@ -176,7 +182,7 @@ EXPORTED_SYMBOLS = ["gen_proof", "zp_last_error", "zp_launch_count", "zp_device_
                     "zp_prover_destroy", "zp_prover_set_label", "zp_profiler_range", "zp_prover_set_stream", "zp_prover_load_srs", "zp_prover_generate_srs",
                     "zp_prover_read_srs", "zp_prover_load_pk", "zp_prover_preprocess", "zp_prover_verifier_key",
                     "zp_prover_prove", "zp_prover_last_timing", "zp_prover_upload_witness", "zp_prover_prove_resident",
-                    "zp_prover_collect_msm_stats", "zp_prover_msm_stats", "zp_prover_set_shard", "zp_prover_set_device_broadcast", "zp_ntt_host", "zp_msm_host", "zp_msm_points_host",
+                    "zp_prover_collect_msm_stats", "zp_prover_msm_stats", "zp_prover_set_shard", "zp_prover_set_device_broadcast", "zp_ntt_host", "zp_ntt_sharded_host", "zp_bench_ntt_sharded", "zp_msm_host", "zp_msm_points_host",
                     "zp_poly_eval_host", "zp_poly_divide_host", "zp_prefix_product_host", "zp_bench_alloc",
                     "zp_bench_upload", "zp_bench_download", "zp_bench_ntt", "zp_bench_msm", "zp_bench_msm_breakdown",
                     "zp_bench_int_pipe"]
@@ -345,6 +351,30 @@ class ProverContext:
         out = np.zeros_like(data)
         self._ck(self.lib.zp_ntt_host(self.h, kind, log_n, as_u64p(data), as_u64p(out)))
         return out
+
+    def _a2a_cb(self, alltoall):
+        def _cb(user, send, recv, nbytes):
+            try:
+                alltoall(send, recv, nbytes)
+                return 0
+            except Exception as e:  # noqa: BLE001
+                self._cb_error = e
+                return 1
+        return DEV_A2A_FN(_cb)
+
+    def ntt_sharded(self, kind, log_n, rank, world, local_in, alltoall):
+        """alltoall(send_ptr: int, recv_ptr: int, bytes_per_peer: int) exchanges device memory between the ranks."""
+        out = np.zeros_like(local_in)
+        cb = self._a2a_cb(alltoall)
+        self._ck(self.lib.zp_ntt_sharded_host(self.h, kind, log_n, rank, world, as_u64p(local_in), as_u64p(out), cb, None))
+        return out
+
+    def bench_ntt_sharded(self, kind, log_n, rank, world, slots, iters, alltoall):
+        ms = ctypes.c_double()
+        cb = self._a2a_cb(alltoall)
+        self._ck(self.lib.zp_bench_ntt_sharded(self.h, kind, log_n, rank, world, slots[0], slots[1], slots[2], slots[3], iters, cb,
+                                               None, ctypes.byref(ms)))
+        return ms.value
 
     def msm(self, scalars):
         out = np.zeros(12, dtype=np.uint64)
