@@ -79,3 +79,37 @@ def test_gen_proof_with_precomputed_msm_tables(pkg, emu_lib, oracle, monkeypatch
     assert np.array_equal(c.msm(sc), oracle.msm(oc.srs(), sc))
     c.close()
     oc.close()
+
+
+@pytest.mark.parametrize("rounds", [1, 3])
+def test_msm_batch_affine_rounds(pkg, emu_lib, oracle, monkeypatch, rounds):
+    """Batch-affine pre-reduction (pairwise affine additions with a shared batch inversion) gives the same point; with
+    repeated input points (x1 == x2 pairs) it must detect the degenerate pair and fall back to the exact XYZZ path."""
+    monkeypatch.setenv("ZP_MSM_BA_ROUNDS", str(rounds))
+    monkeypatch.setenv("ZP_MSM_BA_MIN_LOG", "4")
+    ctx = pkg.ProverContext(8, emu_lib)
+    n = 700
+    pts, _ = oracle.srs(7, n)
+    sc = oracle.random_fr(2, n)
+    sc[3] = 0
+    assert np.array_equal(ctx.msm_points(pts, sc, 6), oracle.msm(pts, sc))
+    pts2, sc2 = pts.copy(), sc.copy()
+    pts2[10:40] = pts2[10]
+    sc2[10:40] = sc2[10]
+    assert np.array_equal(ctx.msm_points(pts2, sc2, 6), oracle.msm(pts2, sc2))
+    ctx.close()
+
+
+def test_gen_proof_with_batch_affine_and_tables(pkg, emu_lib, oracle, monkeypatch):
+    monkeypatch.setenv("ZP_MSM_PRECOMP_MIN_LOG", "8")
+    monkeypatch.setenv("ZP_MSM_BA_ROUNDS", "2")
+    monkeypatch.setenv("ZP_MSM_BA_MIN_LOG", "4")
+    oc = oracle_lib.OracleCircuit(oracle, 3, 42, 7, 0)
+    ref_proof, _ = oc.prove()
+    c = pkg.ProverContext(oc.log_n, emu_lib)
+    c.load_srs(oc.srs())
+    c.preprocess(oc.selector_evals(), oc.tables())
+    circ = pkg.make_circuit(oc.cs_n, oc.lookup_len, oc.pi_pos, oc.q_lookup(), oc.pi_canonical(), *oc.wires())
+    assert np.array_equal(c.prove(circ).to_words(), ref_proof)
+    c.close()
+    oc.close()

@@ -71,17 +71,13 @@ void MsmWorkspace::reserve(size_t n, const MsmConfig& cfg) {
         const char* v = getenv("ZP_ACC_VARIANT");
         if (v) acc_variant = atoi(v);
     }
-    // work-segment length: at most 2x the mean bucket load (so typical buckets are one segment), but short enough
-    // that every persistent thread gets >= 8 segments (load balance on small / sharded inputs), never below 32
-    size_t mean = (wn + wb - 1) / wb;
-    size_t nthreads = (size_t)sm_count * 3 * 128;
-    size_t balanced = wn / (nthreads * 8);
-    seg = 2 * mean;
-    if (balanced < seg) seg = balanced;
-    if (seg < 32) seg = 32;
-    max_segs = wn / seg + wb + 1;
-    if (segs.n < max_segs) segs.alloc(max_segs);
-    if (desc.n < max_segs) desc.alloc(max_segs);
+    if (ba_rounds == 0) {
+        const char* br = getenv("ZP_MSM_BA_ROUNDS");
+        ba_rounds = br ? atoi(br) : 0;  // opt-in: measured 25.3 -> 24.0 ms at 2^22 with 3 rounds (profiles/r01_msm_batch_affine.log)
+        if (ba_rounds <= 0) ba_rounds = -1;  // disabled
+        const char* bm = getenv("ZP_MSM_BA_MIN_LOG");
+        if (bm) ba_min_entries = (size_t)1 << atoi(bm);
+    }
     if (!counter.p) counter.alloc(1);
     size_t np = (size_t)cfg.nsets * msm_reduce_groups(cfg);
     if (partial.n < np) partial.alloc(np);
@@ -285,7 +281,7 @@ __global__ void __launch_bounds__(128, MINBLOCKS) msm_accumulate_kernel(const af
         }
         // (software-pipelining the gather one iteration ahead was measured slower: 32.3 vs 30.1 ms — the loop is
         // multiplier-bound, the extra 24 live registers cost more than the hidden latency)
-        uint32_t e = sorted[k];
+        uint32_t e = sorted ? sorted[k] : k;  // after batch-affine rounds the run IS the point array
         affine_t p = load_affine(&points[e & 0x7fffffffu]);
         if (e >> 31) p.y = p.y.neg();
         acc.add_affine(p.x, p.y);
@@ -396,6 +392,10 @@ void msm_build_table(affine_t* dst, const affine_t* src, size_t n, int c, int nw
                   dst + (size_t)(w - 1) * n, n, c);
 }
 
+}  // namespace zp
+#include "msm_affine.cuh"
+namespace zp {
+
 // final[set] = sum_g partial[set * groups + g]   (one CTA per bucket set)
 __global__ void __launch_bounds__(128) msm_final_kernel(const xyzz_t* __restrict__ partial, int groups, xyzz_t* __restrict__ final_out) {
     __shared__ xyzz_t sm[128];
@@ -415,9 +415,10 @@ __global__ void __launch_bounds__(128) msm_final_kernel(const xyzz_t* __restrict
     if (threadIdx.x == 0) store_xyzz(&final_out[blockIdx.x], sm[0]);
 }
 
-void msm_launch(MsmWorkspace& ws, const MsmConfig& cfg, const affine_t* points, const fr_t* scalars, size_t n, cudaStream_t st) {
+static void msm_launch_impl(MsmWorkspace& ws, const MsmConfig& cfg, const affine_t* points, const fr_t* scalars, size_t n, bool allow_ba,
+                            cudaStream_t st) {
     ws.reserve(n, cfg);
-    const size_t wb = (size_t)cfg.nsets * cfg.nbuckets;
+    const size_t wb = (size_t)cfg.nsets * cfg.nbuckets, wn = (size_t)cfg.nwin * n;
     if (cfg.tab_stride && (size_t)cfg.nwin * cfg.tab_stride >= ((size_t)1 << 31))
         throw std::runtime_error("msm: precomputed table too large for 31-bit indices");
     auto mark = [&](int k) {
@@ -425,6 +426,9 @@ void msm_launch(MsmWorkspace& ws, const MsmConfig& cfg, const affine_t* points, 
         if (!ws.ev[k]) ZP_CUDA(cudaEventCreate(&ws.ev[k]));
         ZP_CUDA(cudaEventRecord(ws.ev[k], st));
     };
+    ws.last_points = points;
+    ws.last_scalars = scalars;
+    ws.last_n = n;
     ZP_CUDA(cudaMemsetAsync(ws.cursor.p, 0, wb * sizeof(uint32_t), st));
     mark(0);
     if (n) {
@@ -438,10 +442,60 @@ void msm_launch(MsmWorkspace& ws, const MsmConfig& cfg, const affine_t* points, 
         ZP_LAUNCH(msm_scatter_kernel, dim3((unsigned)((n + 255) / 256), cfg.nwin), dim3(256), 0, st, ws.digits.p, n, cfg.nwin,
                   cfg.nbuckets, cfg.tab_stride, ws.cursor.p, ws.sorted.p);
     }
-    ZP_LAUNCH(msm_segcount_kernel, dim3((unsigned)((wb + 255) / 256)), dim3(256), 0, st, ws.start.p, ws.cursor.p, wb,
-              (uint32_t)ws.seg, ws.seg_cnt.p);
+    // ---- batch-affine pre-reduction rounds
+    const uint32_t *run_begin = ws.start.p, *run_end = ws.cursor.p, *entries = ws.sorted.p;
+    const affine_t* pts = points;
+    size_t est = wn;  // upper bound on the bucket entries still to be added
+    int rounds = (allow_ba && wn >= ws.ba_min_entries) ? ws.ba_rounds : 0;
+    ws.ba_used = rounds > 0;
+    if (rounds > 0) {
+        size_t cap0 = wn / 2 + wb;
+        if (ws.ba_pts[0].n < cap0) ws.ba_pts[0].alloc(cap0);
+        if (rounds > 1 && ws.ba_pts[1].n < cap0 / 2 + wb) ws.ba_pts[1].alloc(cap0 / 2 + wb);
+        if (ws.ba_den.n < cap0 + cap0 / (BI_CH - 1) + 64) ws.ba_den.alloc(cap0 + cap0 / (BI_CH - 1) + 64);
+        if (ws.ba_src.n < cap0) ws.ba_src.alloc(cap0);
+        if (ws.ba_cnt.n < wb) ws.ba_cnt.alloc(wb);
+        for (int k = 0; k < 2; k++)
+            if (ws.ba_rs[k].n < wb + 1) ws.ba_rs[k].alloc(wb + 1);
+        if (!ws.ba_flag.p) ws.ba_flag.alloc(2);
+        ZP_CUDA(cudaMemsetAsync(ws.ba_flag.p, 0, 2 * sizeof(uint32_t), st));
+        for (int r = 0; r < rounds; r++) {
+            size_t cap = est / 2 + wb;
+            uint32_t* rs = ws.ba_rs[r & 1].p;
+            affine_t* out = ws.ba_pts[r & 1].p;
+            ZP_LAUNCH(ba_pair_count_kernel, dim3((unsigned)((wb + 255) / 256)), dim3(256), 0, st, run_begin, run_end, wb, ws.ba_cnt.p);
+            msm_scan(ws.ba_cnt.p, rs, wb, ws.tile_sum.p, st);
+            ZP_LAUNCH(ba_pair_denoms_kernel, dim3((unsigned)((cap + 255) / 256)), dim3(256), 0, st, run_begin, run_end, rs, wb, cap,
+                      entries, pts, ws.ba_den.p, ws.ba_src.p, ws.ba_flag.p);
+            fq_batch_inverse(ws.ba_den.p, cap, ws.ba_den.p + cap, st);
+            ZP_LAUNCH(ba_pair_sums_kernel, dim3((unsigned)((cap + 255) / 256)), dim3(256), 0, st, ws.ba_src.p, cap, entries, pts,
+                      ws.ba_den.p, out);
+            run_begin = rs;
+            run_end = rs + 1;
+            entries = nullptr;
+            pts = out;
+            est = cap;
+        }
+    }
+    // ---- work segments over the (remaining) runs.  Length: at most 2x the mean bucket load (typical buckets are one
+    // segment) but short enough that every persistent thread gets >= 8 segments; never below 32 (16 after pre-reduction).
+    {
+        size_t mean = (est + wb - 1) / wb;
+        size_t nthreads = (size_t)ws.sm_count * 3 * 128;
+        size_t balanced = est / (nthreads * 8);
+        size_t seg = 2 * mean;
+        if (balanced < seg) seg = balanced;
+        size_t floor_len = rounds > 0 ? 16 : 32;
+        if (seg < floor_len) seg = floor_len;
+        ws.seg = seg;
+        size_t need = est / seg + wb + 1;
+        if (ws.segs.n < need) ws.segs.alloc(need);
+        if (ws.desc.n < need) ws.desc.alloc(need);
+    }
+    ZP_LAUNCH(msm_segcount_kernel, dim3((unsigned)((wb + 255) / 256)), dim3(256), 0, st, run_begin, run_end, wb, (uint32_t)ws.seg,
+              ws.seg_cnt.p);
     msm_scan(ws.seg_cnt.p, ws.seg_start.p, wb, ws.tile_sum.p, st);
-    ZP_LAUNCH(msm_segdesc_kernel, dim3((unsigned)((wb + 255) / 256)), dim3(256), 0, st, ws.start.p, ws.cursor.p, ws.seg_start.p, wb,
+    ZP_LAUNCH(msm_segdesc_kernel, dim3((unsigned)((wb + 255) / 256)), dim3(256), 0, st, run_begin, run_end, ws.seg_start.p, wb,
               (uint32_t)ws.seg, ws.desc.p);
     mark(3);
     {
@@ -451,13 +505,13 @@ void msm_launch(MsmWorkspace& ws, const MsmConfig& cfg, const affine_t* points, 
         unsigned grid = (unsigned)(ws.sm_count * blocks_per_sm);
         if (variant == 4) {
             auto k = msm_accumulate_kernel<4>;
-            ZP_LAUNCH(k, dim3(grid), dim3(128), 0, st, points, ws.sorted.p, ws.desc.p, ws.seg_start.p + wb, ws.counter.p, ws.segs.p);
+            ZP_LAUNCH(k, dim3(grid), dim3(128), 0, st, pts, entries, ws.desc.p, ws.seg_start.p + wb, ws.counter.p, ws.segs.p);
         } else if (variant == 5) {
             auto k = msm_accumulate_kernel<5>;
-            ZP_LAUNCH(k, dim3(grid), dim3(128), 0, st, points, ws.sorted.p, ws.desc.p, ws.seg_start.p + wb, ws.counter.p, ws.segs.p);
+            ZP_LAUNCH(k, dim3(grid), dim3(128), 0, st, pts, entries, ws.desc.p, ws.seg_start.p + wb, ws.counter.p, ws.segs.p);
         } else {
             auto k = msm_accumulate_kernel<3>;
-            ZP_LAUNCH(k, dim3(grid), dim3(128), 0, st, points, ws.sorted.p, ws.desc.p, ws.seg_start.p + wb, ws.counter.p, ws.segs.p);
+            ZP_LAUNCH(k, dim3(grid), dim3(128), 0, st, pts, entries, ws.desc.p, ws.seg_start.p + wb, ws.counter.p, ws.segs.p);
         }
     }
     ZP_LAUNCH(msm_fold_small_kernel, dim3((unsigned)((wb + 127) / 128)), dim3(128), 0, st, ws.segs.p, ws.seg_start.p, wb);
@@ -472,10 +526,29 @@ void msm_launch(MsmWorkspace& ws, const MsmConfig& cfg, const affine_t* points, 
     mark(5);
     ZP_CUDA(cudaMemcpyAsync(ws.partial_host.data(), ws.final_sums.p, (size_t)cfg.nsets * sizeof(xyzz_t),
                             cudaMemcpyDeviceToHost, st));
+    if (ws.ba_used) {
+        // entries the accumulate kernel saw (for the roofline accounting) + the degenerate-pair flag
+        ZP_CUDA(cudaMemcpyAsync(&ws.ba_flag_host[1], run_begin + wb, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        ZP_CUDA(cudaMemcpyAsync(&ws.ba_flag_host[0], ws.ba_flag.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    }
+    ws.acc_entries = (double)wn;
+}
+
+void msm_launch(MsmWorkspace& ws, const MsmConfig& cfg, const affine_t* points, const fr_t* scalars, size_t n, cudaStream_t st) {
+    msm_launch_impl(ws, cfg, points, scalars, n, true, st);
 }
 
 host::G1 msm_collect(MsmWorkspace& ws, const MsmConfig& cfg, cudaStream_t st) {
     ZP_CUDA(cudaStreamSynchronize(st));
+    if (ws.ba_used) {
+        if (ws.ba_flag_host[0]) {
+            // a pair with equal x-coordinates: redo this MSM on the exact XYZZ-only path
+            msm_launch_impl(ws, cfg, ws.last_points, ws.last_scalars, ws.last_n, false, st);
+            ZP_CUDA(cudaStreamSynchronize(st));
+        } else {
+            ws.acc_entries = (double)ws.ba_flag_host[1];
+        }
+    }
     if (ws.timing && ws.ev[5]) {
         for (int k = 0; k < 5; k++) {
             float ms = 0;

@@ -35,6 +35,21 @@ struct MsmWorkspace {
     DevBuf<uint32_t> tile_sum; // scratch of the multi-CTA scan
     int sm_count = 0;
     int acc_variant = 3;       // resident CTAs per SM of the accumulate kernel (ZP_ACC_VARIANT=3|4|5)
+    // batch-affine pre-reduction (msm_affine.cuh): rounds of pairwise affine additions before the XYZZ accumulation
+    int ba_rounds = 0;            // 0 = not read yet, -1 = off (default), > 0 = rounds (ZP_MSM_BA_ROUNDS)
+    size_t ba_min_entries = (size_t)1 << 22;
+    DevBuf<affine_t> ba_pts[2];   // materialised partial sums (ping-pong)
+    DevBuf<fq_t> ba_den;          // denominators -> inverses, followed by the product-tree levels
+    DevBuf<uint32_t> ba_src;      // source index of each output slot
+    DevBuf<uint32_t> ba_cnt, ba_rs[2];
+    DevBuf<uint32_t> ba_flag;     // [0] degenerate pair seen, [1] entries left for the accumulation
+    uint32_t ba_flag_host[2] = {0, 0};
+    bool ba_used = false;
+    double acc_entries = 0;       // bucket entries the accumulate kernel of the last launch processed
+    // arguments of the last launch (to redo it on the plain path if a degenerate pair was seen)
+    const affine_t* last_points = nullptr;
+    const fr_t* last_scalars = nullptr;
+    size_t last_n = 0;
     size_t seg = 0;            // points per work segment (2x the mean bucket load, >= 32)
     size_t max_segs = 0;
     DevBuf<xyzz_t> partial;    // [nwin * MSM_REDUCE_GROUPS]
