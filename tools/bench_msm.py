@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--logs", default="22")
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--ntt", type=int, default=0)
+    ap.add_argument("--no-msm", action="store_true", dest="no_msm")
     args = ap.parse_args()
     pkg = load_package()
     lib = pkg.load_library()
@@ -28,7 +29,7 @@ def main():
     tau = orc.random_fr(7, 1)[0]
     n = 1 << min(lmax, 23)
     x = orc.random_fr(2, n)
-    for lg in logs:
+    for lg in ([] if args.no_msm else logs):
         # one context per size so that window size / precomputed tables are tuned for that size
         m = 1 << lg
         c = pkg.ProverContext(max(lg, 6), lib)

@@ -94,7 +94,7 @@ ZP_D fr_t sm_load(const uint4* sm, int half_stride, int idx) {
     return r;
 }
 
-__global__ void __launch_bounds__(512) ntt_pass_kernel(const fr_t* __restrict__ in, fr_t* __restrict__ out, NttPassParams p) {
+__global__ void __launch_bounds__(1024) ntt_pass_kernel(const fr_t* __restrict__ in, fr_t* __restrict__ out, NttPassParams p) {
     ZP_DYN_SMEM(uint4, sm);
     const int R = 1 << p.lr, C = 1 << p.lc, RC = R * C;
     const int tid = threadIdx.x, nt = blockDim.x;
@@ -219,7 +219,12 @@ void ntt_run(const NttTables& T, NttScratch& S, NttKind kind, int logn, const fr
         pp.logn = logn;
         pp.lr = bits[p];
         int lq = logn - bits[p];  // log2 of number of q values
-        int lc = 12 - bits[p];     // tile of 4096 elements (128 KiB of shared memory)
+        static int tile_log = getenv("ZP_NTT_TILE_LOG") ? atoi(getenv("ZP_NTT_TILE_LOG")) : 10;
+        static int max_threads = getenv("ZP_NTT_THREADS") ? atoi(getenv("ZP_NTT_THREADS")) : 128;
+        // tile of 2^tile_log elements.  Measured on B200 (profiles/r01_ntt_tile_sweep.log): 1024-element (32 KiB) tiles
+        // with 128 threads beat 4096-element tiles with 512 threads by 19 % (2^25 coset NTT 13.2 -> 10.7 ms): seven
+        // resident CTAs per SM hide the barrier + multiplier latency better than one big CTA.
+        int lc = tile_log - bits[p];
         if (lc > lq) lc = lq;
         if (p > 0 && lc > lk) lc = lk;  // C must divide K_done
         if (lc < 0) lc = 0;
@@ -237,7 +242,7 @@ void ntt_run(const NttTables& T, NttScratch& S, NttKind kind, int logn, const fr
         pp.ninv = T.ninv[logn];
         int RC = 1 << (pp.lr + pp.lc);
         size_t smem = (size_t)RC * 32;
-        int threads = RC / 2 < 512 ? (RC / 2 < 32 ? 32 : RC / 2) : 512;
+        int threads = RC / 2 < max_threads ? (RC / 2 < 32 ? 32 : RC / 2) : max_threads;
         unsigned grid = (unsigned)(((size_t)1 << lq) >> lc);
 #ifndef ZP_EMU
         static bool attr_set = false;

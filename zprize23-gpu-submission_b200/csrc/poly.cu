@@ -441,7 +441,7 @@ __global__ void __launch_bounds__(128) quotient_kernel(QuotientArgs a) {
         fr_t id = (ag + bx) * (bg + (b8 - bx)) * (cg + (b8 + b4 + bx)) * (dg + (b16 + bx)) * zi * a.alpha;
         fr_t cp = (ag + a.beta * load_fr(&a.sigma[0][i])) * (bg + a.beta * load_fr(&a.sigma[1][i])) *
                   (cg + a.beta * load_fr(&a.sigma[2][i])) * (dg + a.beta * load_fr(&a.sigma[3][i])) * zn * a.alpha;
-        fr_t l1a = load_fr(&a.l1[i]) * a.alpha.sqr();
+        fr_t l1a = load_fr(&a.l1[i]) * a.alpha_sq;
         total = total + (id - cp) + (zi - one) * l1a;
     }
 

@@ -56,6 +56,7 @@ struct QuotientArgs {
     const fr_t* l1;           // L_1 on the coset (resident, depends on N only)
     const fr_t* sel[15];      // selector coset evaluations in ProverKeyC order; nullptr = identically zero
     const fr_t* sigma[4];
+    fr_t alpha_sq;            // alpha^2 (hoisted out of the kernel)
     fr_t alpha, beta, gamma, delta, epsilon, zeta, range_sep, logic_sep, fixed_sep, var_sep, lookup_sep;
     fr_t vh_inv[8];           // 1 / (g^N w8^k - 1)
     fr_t coeff_d;             // JubJub d

@@ -602,6 +602,7 @@ void Prover::prove_resident(ProofC* out) {
         qa.l1 = l1_coset.p;
         for (int i = 0; i < 15; i++) qa.sel[i] = evals[i].p;
         for (int k = 0; k < 4; k++) qa.sigma[k] = evals[PK_SIGL + k].p;
+        qa.alpha_sq = D(alpha.sqr());
         qa.alpha = D(alpha); qa.beta = D(beta); qa.gamma = D(gamma); qa.delta = D(delta); qa.epsilon = D(epsilon);
         qa.zeta = D(zeta); qa.range_sep = D(range_sep); qa.logic_sep = D(logic_sep); qa.fixed_sep = D(fixed_sep);
         qa.var_sep = D(var_sep); qa.lookup_sep = D(lookup_sep);
