@@ -263,8 +263,16 @@ def main():
 
     # ---- roofline of the dominant kernel (MSM bucket accumulation, integer-pipe bound) + the NTT (HBM)
     achieved = acc_mads / (acc_ms * 1e-3) / 1e12 if acc_ms > 0 else None  # T mad/s
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
+        if world == 1 and args.height == 15:
+            traffic = tj["msm_accumulate_kernel"]["traffic_bytes_per_launch"]  # bytes per launch, one ncu --set full capture
+    except Exception:  # noqa: BLE001
+        pass
     roofline = {"bound": "int32-mad", "kernel": "msm_accumulate_kernel", "achieved": achieved, "peak": int_peak,
-                "unit": "Tmad/s", "frac": (achieved / int_peak) if achieved and int_peak else None, "traffic": None,
+                "unit": "Tmad/s", "frac": (achieved / int_peak) if achieved and int_peak else None, "traffic": traffic,
+                "traffic_unit": "bytes per launch (dram read + write, ncu)",
                 "peak_source": "in-run dependent-free mad.lo.u32 microbenchmark (SURVEY 8d); algorithmic ops = 10*588*M*W",
                 "launches": acc_launch, "avg_launch_ms": acc_ms / max(acc_launch, 1),
                 "share_of_step": acc_ms / args.steps / step_ms}

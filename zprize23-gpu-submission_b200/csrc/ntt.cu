@@ -195,7 +195,7 @@ void ntt_run(const NttTables& T, NttScratch& S, NttKind kind, int logn, const fr
         else ZP_CUDA(cudaMemsetAsync(out, 0, sizeof(fr_t), st));
         return;
     }
-    const int KMAX = 9;
+    static const int KMAX = getenv("ZP_NTT_KMAX") ? atoi(getenv("ZP_NTT_KMAX")) : 9;
     int P = (logn + KMAX - 1) / KMAX;
     int bits[8];
     for (int p = 0; p < P; p++) bits[p] = logn / P + (p < logn % P ? 1 : 0);
@@ -225,6 +225,7 @@ void ntt_run(const NttTables& T, NttScratch& S, NttKind kind, int logn, const fr
         // with 128 threads beat 4096-element tiles with 512 threads by 19 % (2^25 coset NTT 13.2 -> 10.7 ms): seven
         // resident CTAs per SM hide the barrier + multiplier latency better than one big CTA.
         int lc = tile_log - bits[p];
+        if (lc < 0) lc = 0;
         if (lc > lq) lc = lq;
         if (p > 0 && lc > lk) lc = lk;  // C must divide K_done
         if (lc < 0) lc = 0;
