@@ -113,3 +113,21 @@ def test_gen_proof_with_batch_affine_and_tables(pkg, emu_lib, oracle, monkeypatc
     assert np.array_equal(c.prove(circ).to_words(), ref_proof)
     c.close()
     oc.close()
+
+
+def test_edge_cases(ctx, oracle):
+    """Empty / single-element / ragged inputs of the operator entry points."""
+    pts, _ = oracle.srs(7, 4)
+    sc = oracle.random_fr(2, 4)
+    inf = ctx.msm_points(pts[:0].copy(), sc[:0].copy())  # empty MSM = identity in the FFI encoding (0, Mont(1))
+    assert not inf[:6].any() and inf[6] == 0x760900000002fffd
+    assert np.array_equal(ctx.msm_points(pts[:1].copy(), sc[:1].copy()), oracle.msm(pts[:1].copy(), sc[:1].copy()))
+    for n in [1, 2]:
+        x = oracle.random_fr(1, n)
+        for kind in range(4):
+            assert np.array_equal(ctx.ntt(kind, x), oracle.ntt(kind, x))
+    z = oracle.random_fr(4, 1)[0]
+    for n in [1, 5, 33, 64, 65]:
+        x = oracle.random_fr(3, n)
+        assert np.array_equal(ctx.poly_eval(x, z), oracle.poly_eval(x, z))
+        assert np.array_equal(ctx.prefix_product(x)[0], ONE)

@@ -175,3 +175,39 @@ def test_precomputed_table_msm_matches_oracle(pkg, gpu_lib, oracle):
     sc[:100] = 0
     assert np.array_equal(ctx.msm(sc), oracle.msm(pts, sc))
     ctx.close()
+
+
+def test_edge_cases_on_device(ctx16, oracle):
+    pts, _ = oracle.srs(7, 4)
+    sc = oracle.random_fr(2, 4)
+    inf = ctx16.msm_points(pts[:0].copy(), sc[:0].copy())
+    assert not inf[:6].any() and np.array_equal(inf[6:], oracle_fq_one(oracle))
+    for n in [1, 2]:
+        x = oracle.random_fr(1, n)
+        for kind in range(4):
+            assert np.array_equal(ctx16.ntt(kind, x), oracle.ntt(kind, x))
+    z = oracle.random_fr(4, 1)[0]
+    for n in [1, 5, 33, 64, 65]:
+        x = oracle.random_fr(3, n)
+        assert np.array_equal(ctx16.poly_eval(x, z), oracle.poly_eval(x, z))
+
+
+def test_largest_supported_ntt_roundtrip(ctx16, oracle):
+    """2^25 = the 8N extended domain of HEIGHT=15: coset NTT then coset iNTT is the identity; plain NTT is linear."""
+    n = 1 << 25
+    x = oracle.random_fr(21, n)
+    assert np.array_equal(ctx16.ntt(3, ctx16.ntt(2, x)), x)
+
+
+def test_batch_affine_msm_on_device(pkg, gpu_lib, oracle, monkeypatch):
+    monkeypatch.setenv("ZP_MSM_BA_ROUNDS", "3")
+    monkeypatch.setenv("ZP_MSM_BA_MIN_LOG", "10")
+    ctx = pkg.ProverContext(10, gpu_lib)
+    n = 1 << 14
+    pts, _ = oracle.srs(7, n)
+    sc = oracle.random_fr(2, n)
+    assert np.array_equal(ctx.msm_points(pts, sc), oracle.msm(pts, sc))
+    pts[100:164] = pts[100]  # equal points in one bucket: degenerate pair -> exact fallback path
+    sc[100:164] = sc[100]
+    assert np.array_equal(ctx.msm_points(pts, sc), oracle.msm(pts, sc))
+    ctx.close()
