@@ -170,6 +170,16 @@ int zp_prover_set_device_broadcast(zp_prover* p, zp_dev_broadcast_fn bcast, void
  * [4] other (CUDA events on the prover's stream). */
 int zp_prover_last_timing(zp_prover* p, double* out_ms, int n);
 
+/* ---- ark-serialize 0.3 wire format of `Proof<Fr, KZG10<Bls12_381>>` (proof.rs:37-121) --------------------------
+ * 17 compressed G1 commitments (48 B each) || aw_opening (48 B + Option::None byte) || saw_opening (48 B + 1 B) ||
+ * wire(4) / permutation(4) / lookup(8) evaluations (32 B LE canonical each) || custom evaluations as
+ * Vec<(String, Fr)>: u64 count, then (u64 label length, label bytes, 32 B) x 10.  1930 bytes in total.
+ * Host-only helpers (what util.rs:225-291 + CanonicalSerialize do on the Rust side). */
+#define ZP_PROOF_SERIALIZED_BYTES 1930
+int zp_proof_serialize(const ProofC* proof, uint8_t* out, size_t capacity, size_t* written);
+/* Inverse of zp_proof_serialize: decompresses the points (y recovered from x, sign bit) — no subgroup check. */
+int zp_proof_deserialize(const uint8_t* bytes, size_t len, ProofC* out);
+
 /* ---- operator entry points for the sweeps (function.cuh:45-113 equivalents) ------------------ */
 /* kind: 0 NTT, 1 iNTT, 2 coset-NTT (g = 7), 3 coset-iNTT; natural order in/out; host buffers. */
 int zp_ntt_host(zp_prover* p, int kind, int log_n, const uint64_t* in, uint64_t* out);

@@ -257,6 +257,37 @@ void zpo_transcript_script(const char* proto, const uint8_t* script, size_t scri
     }
 }
 
+// ---- ark-serialize 0.3 bytes of Proof<Fr, KZG10<Bls12_381>> (proof.rs:37-121; derive order = declaration order) ----
+// commitments: compressed G1; openings: kzg10::Proof { w, random_v: None } = 48 B + 1 B; evaluations: wire, perm, lookup
+// structs field by field, custom evals as Vec<(String, F)>.
+size_t zpo_proof_serialize(const uint64_t* proof_in, uint8_t* out) {
+    ensure_init();
+    ProofO p = proof_from_bytes(proof_in);
+    uint8_t* o = out;
+    for (int c = 0; c < 17; c++, o += 48) serialize_g1(p.comm[c], o);
+    for (int c = 17; c < 19; c++) {
+        serialize_g1(p.comm[c], o);
+        o += 48;
+        *o++ = 0;  // Option::None
+    }
+    for (int e = 0; e < 16; e++, o += 32) p.eval[e].to_bytes_le(o);
+    static const char* labels[10] = {"q_arith_eval", "q_c_eval", "q_l_eval", "q_r_eval", "q_hl_eval",
+                                     "q_hr_eval", "q_h4_eval", "a_next_eval", "b_next_eval", "d_next_eval"};
+    uint64_t cnt = 10;
+    memcpy(o, &cnt, 8);
+    o += 8;
+    for (int k = 0; k < 10; k++) {
+        uint64_t len = strlen(labels[k]);
+        memcpy(o, &len, 8);
+        o += 8;
+        memcpy(o, labels[k], len);
+        o += len;
+        p.eval[16 + k].to_bytes_le(o);
+        o += 32;
+    }
+    return (size_t)(o - out);
+}
+
 // ---- combine_split (multiset.rs:131-176) ------------------------------------------------------
 int zpo_combine_split(size_t n, const uint64_t* t, const uint64_t* f, uint64_t* h1, uint64_t* h2) {
     ensure_init();

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 SOURCES = ["ntt.cu", "msm.cu", "poly.cu", "prover.cu", "capi.cu"]
-HEADERS = ["ptx_ops.cuh", "field.cuh", "curve.cuh", "common.cuh", "ntt.cuh", "msm.cuh", "poly.cuh", "gates.cuh",
+HEADERS = ["ptx_ops.cuh", "field.cuh", "curve.cuh", "common.cuh", "ntt.cuh", "msm.cuh", "msm_affine.cuh", "poly.cuh", "gates.cuh",
            "host_math.hpp", "transcript.hpp", "prover.cuh"]
 LIB = os.path.join(HERE, "libzprize_b200.so")
 EMU_DIR = os.path.join(ROOT, "tests", "emu")
@@ -60,7 +60,8 @@ def build(verbose=False):
 
 def build_emu():
     deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.join(EMU_DIR, "cuda_emu.h"),
-                                                                  os.path.join(EMU_DIR, "cuda_emu.cpp")]
+                                                                  os.path.join(EMU_DIR, "cuda_emu.cpp"),
+                                                                  os.path.join(ROOT, "include", "zprize_b200.h")]
     if not _newer_than(EMU_LIB, deps):
         return EMU_LIB
     cxx = os.environ.get("ZP_CXX", "g++")

@@ -203,6 +203,141 @@ ProofC gen_proof(CircuitC circuit, ProverKeyC pk, CommitKeyC ck) {
     return proof;
 }
 
+// ---- ark-serialize proof I/O (host only) ------------------------------------------------------------
+namespace {
+const char* const kCustomLabels[10] = {"q_arith_eval", "q_c_eval", "q_l_eval", "q_r_eval", "q_hl_eval",
+                                       "q_hr_eval", "q_h4_eval", "a_next_eval", "b_next_eval", "d_next_eval"};
+void put_g1(const CommitmentC& c, uint8_t* out) {
+    host::Fq x, y;
+    memcpy(x.v, c.x, 48);
+    memcpy(y.v, c.y, 48);
+    memset(out, 0, 48);
+    if (x.is_zero() && y == host::Fq::one()) {  // FFI encoding of the identity
+        out[47] |= 0x40;
+        return;
+    }
+    uint64_t cx[6], cy[6], cny[6];
+    x.to_canonical(cx);
+    y.to_canonical(cy);
+    y.neg().to_canonical(cny);
+    memcpy(out, cx, 48);
+    for (int i = 5; i >= 0; i--) {
+        if (cy[i] != cny[i]) {
+            if (cy[i] > cny[i]) out[47] |= 0x80;
+            break;
+        }
+    }
+}
+void get_g1(const uint8_t* in, CommitmentC* c) {
+    uint8_t b[48];
+    memcpy(b, in, 48);
+    bool inf = b[47] & 0x40, positive = b[47] & 0x80;
+    b[47] &= 0x3f;
+    if (inf) {
+        host::Fq one = host::Fq::one();
+        memset(c->x, 0, 48);
+        memcpy(c->y, one.v, 48);
+        return;
+    }
+    uint64_t cx[6];
+    memcpy(cx, b, 48);
+    host::Fq x = host::Fq::from_canonical(cx);
+    host::Fq rhs = x.sqr() * x + host::Fq::from_u64(4);
+    // q = 3 mod 4: sqrt = rhs^((q+1)/4)
+    uint64_t e[6];
+    memcpy(e, host::Params<6>::p(), 48);
+    e[0] += 1;  // no carry: low limb of q ends in ...aaab
+    for (int i = 0; i < 6; i++) e[i] = (e[i] >> 2) | (i < 5 ? e[i + 1] << 62 : 0);
+    host::Fq y = rhs.pow(e, 6);
+    if (y.sqr() != rhs) throw std::runtime_error("zp_proof_deserialize: x is not on the curve");
+    uint64_t cy[6], cny[6];
+    y.to_canonical(cy);
+    y.neg().to_canonical(cny);
+    bool y_greater = false;
+    for (int i = 5; i >= 0; i--) {
+        if (cy[i] != cny[i]) {
+            y_greater = cy[i] > cny[i];
+            break;
+        }
+    }
+    if (y_greater != positive) y = y.neg();
+    memcpy(c->x, x.v, 48);
+    memcpy(c->y, y.v, 48);
+}
+void put_fr(const uint64_t* mont, uint8_t* out) {
+    host::Fr f;
+    memcpy(f.v, mont, 32);
+    uint64_t c[4];
+    f.to_canonical(c);
+    memcpy(out, c, 32);
+}
+void get_fr(const uint8_t* in, uint64_t* mont) {
+    uint64_t c[4];
+    memcpy(c, in, 32);
+    host::Fr f = host::Fr::from_canonical(c);
+    memcpy(mont, f.v, 32);
+}
+}  // namespace
+
+extern "C" int zp_proof_serialize(const ProofC* proof, uint8_t* out, size_t capacity, size_t* written) {
+    return guard([&] {
+        if (capacity < ZP_PROOF_SERIALIZED_BYTES) throw std::runtime_error("zp_proof_serialize: buffer too small");
+        const CommitmentC* comm = &proof->a_comm;
+        uint8_t* p = out;
+        for (int i = 0; i < 17; i++, p += 48) put_g1(comm[i], p);
+        for (int i = 17; i < 19; i++) {  // kzg10::Proof { w, random_v: None }
+            put_g1(comm[i], p);
+            p += 48;
+            *p++ = 0;
+        }
+        const uint64_t* ev = reinterpret_cast<const uint64_t*>(&proof->evaluations);
+        for (int i = 0; i < 16; i++, p += 32) put_fr(ev + 4 * i, p);
+        uint64_t cnt = 10;
+        memcpy(p, &cnt, 8);
+        p += 8;
+        for (int i = 0; i < 10; i++) {
+            uint64_t len = strlen(kCustomLabels[i]);
+            memcpy(p, &len, 8);
+            p += 8;
+            memcpy(p, kCustomLabels[i], len);
+            p += len;
+            put_fr(ev + 4 * (16 + i), p);
+            p += 32;
+        }
+        if ((size_t)(p - out) != ZP_PROOF_SERIALIZED_BYTES) throw std::runtime_error("zp_proof_serialize: size mismatch");
+        if (written) *written = p - out;
+    });
+}
+extern "C" int zp_proof_deserialize(const uint8_t* bytes, size_t len, ProofC* out) {
+    return guard([&] {
+        if (len != ZP_PROOF_SERIALIZED_BYTES) throw std::runtime_error("zp_proof_deserialize: unexpected length");
+        CommitmentC* comm = &out->a_comm;
+        const uint8_t* p = bytes;
+        for (int i = 0; i < 17; i++, p += 48) get_g1(p, &comm[i]);
+        for (int i = 17; i < 19; i++) {
+            get_g1(p, &comm[i]);
+            p += 48;
+            if (*p++ != 0) throw std::runtime_error("zp_proof_deserialize: hiding openings (random_v = Some) are not supported");
+        }
+        uint64_t* ev = reinterpret_cast<uint64_t*>(&out->evaluations);
+        for (int i = 0; i < 16; i++, p += 32) get_fr(p, ev + 4 * i);
+        uint64_t cnt;
+        memcpy(&cnt, p, 8);
+        p += 8;
+        if (cnt != 10) throw std::runtime_error("zp_proof_deserialize: expected 10 custom evaluations");
+        for (int i = 0; i < 10; i++) {
+            uint64_t l;
+            memcpy(&l, p, 8);
+            p += 8;
+            if (l != strlen(kCustomLabels[i]) || memcmp(p, kCustomLabels[i], l) != 0)
+                throw std::runtime_error("zp_proof_deserialize: unexpected custom evaluation label");
+            p += l;
+            get_fr(p, ev + 4 * (16 + i));
+            p += 32;
+        }
+    });
+}
+
 // ---- operator entry points ---------------------------------------------------------------------
 int zp_ntt_host(zp_prover* p, int kind, int log_n, const uint64_t* in, uint64_t* out) {
     return guard([&] {

@@ -168,6 +168,8 @@ def load_library(path=None):
         "zp_bench_msm": (ci, [vp, ci, cs, ci, dp, u64p]),
         "zp_bench_msm_breakdown": (ci, [vp, dp]),
         "zp_bench_int_pipe": (ci, [vp, ci, dp]),
+        "zp_proof_serialize": (ci, [ctypes.POINTER(ProofC), ctypes.c_char_p, cs, ctypes.POINTER(cs)]),
+        "zp_proof_deserialize": (ci, [ctypes.c_char_p, cs, ctypes.POINTER(ProofC)]),
         "gen_proof": (ProofC, [CircuitC, ProverKeyC, CommitKeyC]),
     }
     for name, (res, args) in sig.items():
@@ -178,7 +180,7 @@ def load_library(path=None):
     return lib
 
 
-EXPORTED_SYMBOLS = ["gen_proof", "zp_last_error", "zp_launch_count", "zp_device_available", "zp_prover_create",
+EXPORTED_SYMBOLS = ["gen_proof", "zp_proof_serialize", "zp_proof_deserialize", "zp_last_error", "zp_launch_count", "zp_device_available", "zp_prover_create",
                     "zp_prover_destroy", "zp_prover_set_label", "zp_profiler_range", "zp_prover_set_stream", "zp_prover_load_srs", "zp_prover_generate_srs",
                     "zp_prover_read_srs", "zp_prover_load_pk", "zp_prover_preprocess", "zp_prover_verifier_key",
                     "zp_prover_prove", "zp_prover_last_timing", "zp_prover_upload_witness", "zp_prover_prove_resident",
@@ -220,6 +222,27 @@ def make_prover_key(coeffs, evals, tables, linear_evaluations=None, v_h_coset_8n
     pk.v_h_coset_8n = as_u64p(v_h_coset_8n)
     pk._keep = (keep, tables, linear_evaluations, v_h_coset_8n)
     return pk
+
+
+PROOF_SERIALIZED_BYTES = 1930
+
+
+def proof_serialize(proof, lib=None):
+    """ark-serialize 0.3 bytes of `Proof<Fr, KZG10<Bls12_381>>` (what `CanonicalSerialize` gives the Rust side)."""
+    lib = lib or load_library()
+    buf = ctypes.create_string_buffer(PROOF_SERIALIZED_BYTES)
+    n = ctypes.c_size_t()
+    if lib.zp_proof_serialize(ctypes.byref(proof), buf, PROOF_SERIALIZED_BYTES, ctypes.byref(n)) != 0:
+        raise ZprizeError(lib.zp_last_error().decode())
+    return buf.raw[:n.value]
+
+
+def proof_deserialize(data, lib=None):
+    lib = lib or load_library()
+    proof = ProofC()
+    if lib.zp_proof_deserialize(data, len(data), ctypes.byref(proof)) != 0:
+        raise ZprizeError(lib.zp_last_error().decode())
+    return proof
 
 
 def gen_proof(circuit, pk, ck, lib=None):
