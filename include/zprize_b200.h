@@ -201,6 +201,9 @@ int zp_msm_points_host(zp_prover* p, const uint64_t* points, const uint64_t* sca
 int zp_poly_eval_host(zp_prover* p, const uint64_t* coeffs, size_t n, const uint64_t* point, uint64_t* out);
 /* floor(p / (X - z)) for a host coefficient array (n - 1 coefficients out) */
 int zp_poly_divide_host(zp_prover* p, const uint64_t* coeffs, size_t n, const uint64_t* point, uint64_t* out);
+/* plookup MultiSet::combine_split(t, f) (lookup/multiset.rs:131-176) on the device: n-element host arrays t, f in,
+ * h1, h2 out.  Returns 0, or -1 with "ElementNotIndexed" when an element of f is missing from t. */
+int zp_combine_split_host(zp_prover* p, const uint64_t* t, const uint64_t* f, size_t n, uint64_t* h1, uint64_t* h2);
 /* exclusive prefix product (the z(X) scan primitive) */
 int zp_prefix_product_host(zp_prover* p, const uint64_t* in, size_t n, uint64_t* out);
 

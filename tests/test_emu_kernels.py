@@ -131,3 +131,26 @@ def test_edge_cases(ctx, oracle):
         x = oracle.random_fr(3, n)
         assert np.array_equal(ctx.poly_eval(x, z), oracle.poly_eval(x, z))
         assert np.array_equal(ctx.prefix_product(x)[0], ONE)
+
+
+def _fr_small(oracle, vals):
+    a = np.zeros((len(vals), 4), dtype=np.uint64)
+    a[:, 0] = vals
+    return oracle.fr_op(5, a)
+
+
+def test_combine_split_device(ctx, oracle, pkg):
+    """plookup combine_split on the device vs the oracle (multiset.rs:131-176), incl. the doc example and the error."""
+    h1, h2 = ctx.combine_split(_fr_small(oracle, [2, 4, 1, 3]), _fr_small(oracle, [2, 3, 3, 2]))
+    assert np.array_equal(h1, _fr_small(oracle, [2, 2, 1, 3])) and np.array_equal(h2, _fr_small(oracle, [2, 4, 3, 3]))
+    rng = np.random.default_rng(5)
+    n = 1000
+    tv = rng.integers(0, 300, n)          # many repeated table values, arbitrary order
+    fv = rng.choice(tv, n)
+    t, f = _fr_small(oracle, tv), _fr_small(oracle, fv)
+    ok, o1, o2 = oracle.combine_split(t, f)
+    assert ok
+    h1, h2 = ctx.combine_split(t, f)
+    assert np.array_equal(h1, o1) and np.array_equal(h2, o2)
+    with pytest.raises(pkg.ZprizeError, match="ElementNotIndexed"):
+        ctx.combine_split(_fr_small(oracle, [2, 4, 1, 3]), _fr_small(oracle, [2, 3, 5, 2]))

@@ -211,3 +211,21 @@ def test_batch_affine_msm_on_device(pkg, gpu_lib, oracle, monkeypatch):
     sc[100:164] = sc[100]
     assert np.array_equal(ctx.msm_points(pts, sc), oracle.msm(pts, sc))
     ctx.close()
+
+
+def test_combine_split_on_device(ctx16, oracle, pkg):
+    def small(vals):
+        a = np.zeros((len(vals), 4), dtype=np.uint64)
+        a[:, 0] = vals
+        return oracle.fr_op(5, a)
+    rng = np.random.default_rng(6)
+    n = 1 << 14
+    tv = rng.integers(0, 5000, n)
+    fv = rng.choice(tv, n)
+    t, f = small(tv), small(fv)
+    ok, o1, o2 = oracle.combine_split(t, f)
+    assert ok
+    h1, h2 = ctx16.combine_split(t, f)
+    assert np.array_equal(h1, o1) and np.array_equal(h2, o2)
+    with pytest.raises(pkg.ZprizeError, match="ElementNotIndexed"):
+        ctx16.combine_split(small([2, 4, 1, 3]), small([2, 3, 5, 2]))

@@ -439,6 +439,19 @@ int zp_poly_divide_host(zp_prover* p, const uint64_t* coeffs, size_t n, const ui
         ZP_CUDA(cudaStreamSynchronize(pr->st));
     });
 }
+int zp_combine_split_host(zp_prover* p, const uint64_t* t, const uint64_t* f, size_t n, uint64_t* h1, uint64_t* h2) {
+    return guard([&] {
+        Prover* pr = P(p);
+        DevBuf<fr_t> dt(n), df(n), d1(n), d2(n);
+        ZP_CUDA(cudaMemcpyAsync(dt.p, t, n * sizeof(fr_t), cudaMemcpyHostToDevice, pr->st));
+        ZP_CUDA(cudaMemcpyAsync(df.p, f, n * sizeof(fr_t), cudaMemcpyHostToDevice, pr->st));
+        if (!combine_split(pr->CS, dt.p, df.p, n, d1.p, d2.p, pr->st))
+            throw std::runtime_error("combine_split: ElementNotIndexed (an element of f is not in t)");
+        ZP_CUDA(cudaMemcpyAsync(h1, d1.p, n * sizeof(fr_t), cudaMemcpyDeviceToHost, pr->st));
+        ZP_CUDA(cudaMemcpyAsync(h2, d2.p, n * sizeof(fr_t), cudaMemcpyDeviceToHost, pr->st));
+        ZP_CUDA(cudaStreamSynchronize(pr->st));
+    });
+}
 int zp_prefix_product_host(zp_prover* p, const uint64_t* in, size_t n, uint64_t* out) {
     return guard([&] {
         Prover* pr = P(p);

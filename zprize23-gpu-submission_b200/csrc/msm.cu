@@ -186,7 +186,11 @@ __global__ void __launch_bounds__(256) msm_scan_apply_kernel(uint32_t* __restric
         run += v[k];
     }
 }
+void u32_exclusive_scan(uint32_t* cnt, uint32_t* start, size_t m, uint32_t* tile_sum, cudaStream_t st);
 static void msm_scan(uint32_t* cnt, uint32_t* start, size_t m, uint32_t* tile_sum, cudaStream_t st) {
+    u32_exclusive_scan(cnt, start, m, tile_sum, st);
+}
+void u32_exclusive_scan(uint32_t* cnt, uint32_t* start, size_t m, uint32_t* tile_sum, cudaStream_t st) {
     size_t ntiles = (m + SCAN_TILE - 1) / SCAN_TILE;
     ZP_LAUNCH(msm_scan_tiles_kernel, dim3((unsigned)ntiles), dim3(256), 0, st, cnt, m, tile_sum);
     ZP_LAUNCH(msm_scan_sums_kernel, dim3(1), dim3(1024), 0, st, tile_sum, ntiles, start + m);

@@ -16,6 +16,8 @@ struct MsmConfig {
     size_t tab_stride;  // 0, or the row stride of a precomputed table [w][i] = 2^(c w) * P_i
 };
 MsmConfig msm_config_for(size_t n, int c_override = 0);
+// start[0..m] = exclusive scan of cnt[0..m) (cnt is overwritten with the same prefix); tile_sum: m/2048 + 2 words of scratch
+void u32_exclusive_scan(uint32_t* cnt, uint32_t* start, size_t m, uint32_t* tile_sum, cudaStream_t st);
 // Precomputed-window variant: with T[w][i] = 2^(c w) P_i resident, every window digit of every scalar goes into ONE
 // bucket set, so c can grow (fewer windows => fewer bucket additions) without multiplying the bucket count.
 MsmConfig msm_config_precomp(size_t n, size_t tab_stride);

@@ -384,6 +384,99 @@ __global__ void fill_kernel(fr_t* out, fr_t v, size_t n) {
 }
 void fill(fr_t* out, const fr_t& v, size_t n, cudaStream_t st) { ZP_LAUNCH(fill_kernel, ew_grid(n), dim3(EW_BLOCK), 0, st, out, v, n); }
 
+// ------------------------------------------------------------------ plookup combine_split on the device
+static const uint32_t HS_EMPTY = 0xffffffffu;
+ZP_D uint32_t fr_hash(const fr_t& v) {
+    uint32_t h = v.l[0] * 0x9e3779b1u;
+    h ^= (v.l[1] + 0x7f4a7c15u) * 0x85ebca6bu;
+    h ^= (v.l[3] ^ (h >> 15)) * 0xc2b2ae35u;
+    h ^= v.l[6] * 0x27d4eb2fu;
+    return h ^ (h >> 16);
+}
+__global__ void cs_zero_counts_kernel(uint32_t* __restrict__ table, size_t slots) {
+    size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < slots) table[2 * s + 1] = 0;
+}
+// table[2s] = smallest index in t holding this value, table[2s+1] = occurrences in t and f
+__global__ void cs_insert_t_kernel(const fr_t* __restrict__ t, size_t n, uint32_t* __restrict__ table, uint32_t mask) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fr_t v = load_fr(&t[i]);
+    uint32_t s = fr_hash(v) & mask;
+    while (true) {
+        uint32_t old = atomicCAS(&table[2 * s], HS_EMPTY, (uint32_t)i);
+        if (old == HS_EMPTY || load_fr(&t[old]) == v) {
+            if (old != HS_EMPTY) atomicMin(&table[2 * s], (uint32_t)i);
+            atomicAdd(&table[2 * s + 1], 1u);
+            return;
+        }
+        s = (s + 1) & mask;
+    }
+}
+__global__ void cs_count_f_kernel(const fr_t* __restrict__ f, size_t n, const fr_t* __restrict__ t, uint32_t* __restrict__ table,
+                                  uint32_t mask, uint32_t* __restrict__ err) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fr_t v = load_fr(&f[i]);
+    uint32_t s = fr_hash(v) & mask;
+    while (true) {
+        uint32_t idx = table[2 * s];
+        if (idx == HS_EMPTY) {
+            *err = 1;  // Error::ElementNotIndexed
+            return;
+        }
+        if (load_fr(&t[idx]) == v) {
+            atomicAdd(&table[2 * s + 1], 1u);
+            return;
+        }
+        s = (s + 1) & mask;
+    }
+}
+// cnt[first index] = bucket size
+__global__ void cs_emit_counts_kernel(const uint32_t* __restrict__ table, size_t slots, uint32_t* __restrict__ cnt) {
+    size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= slots) return;
+    uint32_t idx = table[2 * s];
+    if (idx != HS_EMPTY) cnt[idx] = table[2 * s + 1];
+}
+// position p of the sorted union belongs to the bucket i with offs[i] <= p < offs[i+1]; even p -> h1, odd p -> h2
+__global__ void cs_expand_kernel(const fr_t* __restrict__ t, const uint32_t* __restrict__ offs, size_t n, fr_t* __restrict__ h1,
+                                 fr_t* __restrict__ h2) {
+    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= 2 * n) return;
+    size_t lo = 0, hi = n;  // largest i < n with offs[i] <= p
+    while (hi - lo > 1) {
+        size_t mid = (lo + hi) >> 1;
+        if (offs[mid] <= (uint32_t)p) lo = mid; else hi = mid;
+    }
+    fr_t v = load_fr(&t[lo]);
+    store_fr((p & 1) ? &h2[p >> 1] : &h1[p >> 1], v);
+}
+bool combine_split(CombineSplitScratch& S, const fr_t* t, const fr_t* f, size_t n, fr_t* h1, fr_t* h2, cudaStream_t st) {
+    size_t slots = 1;
+    while (slots < 2 * n) slots <<= 1;
+    if (S.table.n < 2 * slots) S.table.alloc(2 * slots);
+    if (S.cnt.n < n) S.cnt.alloc(n);
+    if (S.offs.n < n + 1) S.offs.alloc(n + 1);
+    if (S.tile_sum.n < n / 2048 + 2) S.tile_sum.alloc(n / 2048 + 2);
+    if (!S.flag.p) S.flag.alloc(1);
+    // (idx, cnt) pairs: idx = EMPTY (all ones), cnt = 0
+    ZP_CUDA(cudaMemsetAsync(S.table.p, 0xff, 2 * slots * sizeof(uint32_t), st));
+    ZP_CUDA(cudaMemsetAsync(S.cnt.p, 0, n * sizeof(uint32_t), st));
+    ZP_CUDA(cudaMemsetAsync(S.flag.p, 0, sizeof(uint32_t), st));
+    ZP_LAUNCH(cs_zero_counts_kernel, ew_grid(slots), dim3(EW_BLOCK), 0, st, S.table.p, slots);
+    ZP_LAUNCH(cs_insert_t_kernel, ew_grid(n), dim3(EW_BLOCK), 0, st, t, n, S.table.p, (uint32_t)(slots - 1));
+    ZP_LAUNCH(cs_count_f_kernel, ew_grid(n), dim3(EW_BLOCK), 0, st, f, n, t, S.table.p, (uint32_t)(slots - 1), S.flag.p);
+    ZP_LAUNCH(cs_emit_counts_kernel, ew_grid(slots), dim3(EW_BLOCK), 0, st, S.table.p, slots, S.cnt.p);
+    u32_exclusive_scan(S.cnt.p, S.offs.p, n, S.tile_sum.p, st);
+    uint32_t err = 0;
+    ZP_CUDA(cudaMemcpyAsync(&err, S.flag.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    ZP_CUDA(cudaStreamSynchronize(st));
+    if (err) return false;
+    ZP_LAUNCH(cs_expand_kernel, ew_grid(2 * n), dim3(EW_BLOCK), 0, st, t, S.offs.p, n, h1, h2);
+    return true;
+}
+
 // ------------------------------------------------------------------ fused quotient pass
 // One thread per point of the 8N coset.  Reads every stream once (the "+8" rotations hit lines that
 // are already on their way through L2), evaluates gate + permutation + lookup constraints and multiplies

@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include "ntt.cuh"
 #include "host_math.hpp"
+#include "msm.cuh"
 
 namespace zp {
 
@@ -41,6 +42,15 @@ void lincomb(fr_t* out, const fr_t* const* polys, const fr_t* scalars, int count
 bool all_zero(PolyScratch& S, const fr_t* a, size_t n, cudaStream_t st);
 bool all_equal_to_first(PolyScratch& S, const fr_t* a, size_t n, cudaStream_t st);
 void fill(fr_t* out, const fr_t& v, size_t n, cudaStream_t st);
+
+// h1, h2 = MultiSet::combine_split(t, f) on the device (lookup/multiset.rs:131-176): the multiset union of t and f
+// ordered by first occurrence in t, split into its even- and odd-indexed halves.  Returns false when an element of f
+// is not in t (Error::ElementNotIndexed).  The reference's native code skips this step (gen_proof.cuh:107-115).
+struct CombineSplitScratch {
+    DevBuf<uint32_t> table;   // open-addressing hash table: (first index, count) pairs
+    DevBuf<uint32_t> cnt, offs, tile_sum, flag;
+};
+bool combine_split(CombineSplitScratch& S, const fr_t* t, const fr_t* f, size_t n, fr_t* h1, fr_t* h2, cudaStream_t st);
 
 struct QuotientArgs {
     int logn;                 // log2 N (the 8N coset has 2^(logn+3) points)

@@ -6,7 +6,6 @@
 #include "prover.cuh"
 #include "gates.cuh"
 #include <algorithm>
-#include <unordered_map>
 
 namespace zp {
 
@@ -361,48 +360,6 @@ void Prover::verifier_key(uint64_t* out23) {
     }
 }
 
-// lookup/multiset.rs:131-176 on the host (general plookup tables; the Merkle circuit never gets here)
-static void combine_split_host(const std::vector<fr_t>& t, const std::vector<fr_t>& f, std::vector<fr_t>& h1, std::vector<fr_t>& h2) {
-    struct Key {
-        uint64_t v[4];
-        bool operator==(const Key& o) const { return memcmp(v, o.v, 32) == 0; }
-    };
-    struct KeyHash {
-        size_t operator()(const Key& k) const { return (size_t)(k.v[0] * 0x9e3779b97f4a7c15ULL ^ k.v[1] ^ (k.v[2] << 7) ^ (k.v[3] >> 3)); }
-    };
-    std::unordered_map<Key, size_t, KeyHash> index;
-    std::vector<fr_t> order;
-    std::vector<size_t> count;
-    auto key = [](const fr_t& x) { Key k; memcpy(k.v, x.l, 32); return k; };
-    for (const fr_t& e : t) {
-        auto it = index.find(key(e));
-        if (it == index.end()) {
-            index.emplace(key(e), order.size());
-            order.push_back(e);
-            count.push_back(1);
-        } else {
-            count[it->second]++;
-        }
-    }
-    for (const fr_t& e : f) {
-        auto it = index.find(key(e));
-        if (it == index.end()) throw std::runtime_error("lookup: query element not in table (Error::ElementNotIndexed)");
-        count[it->second]++;
-    }
-    h1.clear();
-    h2.clear();
-    int parity = 0;
-    for (size_t k = 0; k < order.size(); k++) {
-        size_t half = count[k] / 2;
-        h1.insert(h1.end(), half, order[k]);
-        h2.insert(h2.end(), half, order[k]);
-        if (count[k] & 1) {
-            if (parity) { h2.push_back(order[k]); parity = 0; }
-            else { h1.push_back(order[k]); parity = 1; }
-        }
-    }
-}
-
 static inline fr_t D(const Fr& a) { return host::to_dev(a); }
 static inline Fr H(const fr_t& a) { return host::to_host(a); }
 static void put_fr(uint64_t* dst, const Fr& a) { memcpy(dst, a.v, 32); }
@@ -478,19 +435,13 @@ void Prover::prove_resident(ProofC* out) {
               ntt_run(T, NS, NTT_INV, logn, f_ev.p, n, f_poly.p, st); }
             commit(f_poly.p, n, &comm[5], &x, &y, &inf);
             tr.append_point("f", x, y, inf);
-            // h1, h2 = combine_split(t, f): host merge (general plookup path)
-            std::vector<fr_t> ht(n), hf(n), hh1, hh2;
-            ZP_CUDA(cudaMemcpyAsync(ht.data(), t_ev.p, n * sizeof(fr_t), cudaMemcpyDeviceToHost, st));
-            ZP_CUDA(cudaMemcpyAsync(hf.data(), f_ev.p, n * sizeof(fr_t), cudaMemcpyDeviceToHost, st));
-            ZP_CUDA(cudaStreamSynchronize(st));
-            combine_split_host(ht, hf, hh1, hh2);
-            if (hh1.size() != n || hh2.size() != n) throw std::runtime_error("lookup: combine_split produced uneven halves");
-            ZP_CUDA(cudaMemcpyAsync(h1_ev.p, hh1.data(), n * sizeof(fr_t), cudaMemcpyHostToDevice, st));
-            ZP_CUDA(cudaMemcpyAsync(h2_ev.p, hh2.data(), n * sizeof(fr_t), cudaMemcpyHostToDevice, st));
+            // h1, h2 = combine_split(t, f) on the device (hash table keyed by the table value, ordered by first occurrence)
+            { Scope s(CAT_OTHER);
+              if (!combine_split(CS, t_ev.p, f_ev.p, n, h1_ev.p, h2_ev.p, st))
+                  throw std::runtime_error("lookup: query element not in table (Error::ElementNotIndexed)"); }
             { Scope s(CAT_NTT);
               ntt_run(T, NS, NTT_INV, logn, h1_ev.p, n, h1_poly.p, st);
               ntt_run(T, NS, NTT_INV, logn, h2_ev.p, n, h2_poly.p, st); }
-            ZP_CUDA(cudaStreamSynchronize(st));  // hh1/hh2 go out of scope
             commit(h1_poly.p, n, &comm[6], &x, &y, &inf);
             tr.append_point("h1", x, y, inf);
             commit(h2_poly.p, n, &comm[7], &x, &y, &inf);

@@ -28,6 +28,7 @@ struct Prover {
     NttTables T;
     NttScratch NS;
     PolyScratch PS;
+    CombineSplitScratch CS;
     MsmWorkspace MW;
 
     // ---- resident inputs (uploaded / built once, reused by every proof)

@@ -161,6 +161,7 @@ def load_library(path=None):
         "zp_poly_eval_host": (ci, [vp, u64p, cs, u64p, u64p]),
         "zp_poly_divide_host": (ci, [vp, u64p, cs, u64p, u64p]),
         "zp_prefix_product_host": (ci, [vp, u64p, cs, u64p]),
+        "zp_combine_split_host": (ci, [vp, u64p, u64p, cs, u64p, u64p]),
         "zp_bench_alloc": (ci, [vp, ci, cs]),
         "zp_bench_upload": (ci, [vp, ci, u64p, cs]),
         "zp_bench_download": (ci, [vp, ci, u64p, cs]),
@@ -185,7 +186,7 @@ EXPORTED_SYMBOLS = ["gen_proof", "zp_proof_serialize", "zp_proof_deserialize", "
                     "zp_prover_read_srs", "zp_prover_load_pk", "zp_prover_preprocess", "zp_prover_verifier_key",
                     "zp_prover_prove", "zp_prover_last_timing", "zp_prover_upload_witness", "zp_prover_prove_resident",
                     "zp_prover_collect_msm_stats", "zp_prover_msm_stats", "zp_prover_set_shard", "zp_prover_set_device_broadcast", "zp_ntt_host", "zp_ntt_sharded_host", "zp_bench_ntt_sharded", "zp_msm_host", "zp_msm_points_host",
-                    "zp_poly_eval_host", "zp_poly_divide_host", "zp_prefix_product_host", "zp_bench_alloc",
+                    "zp_poly_eval_host", "zp_poly_divide_host", "zp_prefix_product_host", "zp_combine_split_host", "zp_bench_alloc",
                     "zp_bench_upload", "zp_bench_download", "zp_bench_ntt", "zp_bench_msm", "zp_bench_msm_breakdown",
                     "zp_bench_int_pipe"]
 
@@ -419,6 +420,11 @@ class ProverContext:
         out = np.zeros((coeffs.shape[0] - 1, 4), dtype=np.uint64)
         self._ck(self.lib.zp_poly_divide_host(self.h, as_u64p(coeffs), coeffs.shape[0], as_u64p(point), as_u64p(out)))
         return out
+
+    def combine_split(self, t, f):
+        h1, h2 = np.zeros_like(t), np.zeros_like(t)
+        self._ck(self.lib.zp_combine_split_host(self.h, as_u64p(t), as_u64p(f), t.shape[0], as_u64p(h1), as_u64p(h2)))
+        return h1, h2
 
     def prefix_product(self, data):
         out = np.zeros_like(data)
