@@ -217,8 +217,8 @@ int zp_bench_ntt(zp_prover* p, int kind, int log_n, int slot_in, int slot_out, i
 int zp_bench_msm(zp_prover* p, int slot, size_t n, int iters, double* ms, uint64_t* out_affine);
 /* per-kernel device time of the last zp_bench_msm iteration: digits, scan, scatter, accumulate, reduce */
 int zp_bench_msm_breakdown(zp_prover* p, double* ms5);
-/* integer-pipe microbenchmark: mode 0 = IMAD (mad.lo), 1 = IMAD.WIDE (mad.wide), 2 = Fq Montgomery
- * products; returns giga-operations per second (ops = instructions for 0/1, field products for 2) */
+/* integer-pipe microbenchmark: mode 0 = IMAD (mad.lo), 1 = IMAD.WIDE (mad.wide), 2 = Fq Montgomery products,
+ * 3 = Fq Montgomery squarings; returns giga-operations per second (instructions for 0/1, field operations for 2/3) */
 int zp_bench_int_pipe(zp_prover* p, int mode, double* gops);
 
 #ifdef __cplusplus
