@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--ntt", type=int, default=0)
     ap.add_argument("--no-msm", action="store_true", dest="no_msm")
+    ap.add_argument("--dist", default="uniform", help="uniform | witness (50%% zeros, 25%% values < 2^16, 25%% uniform; SURVEY 8d config 3)")
     args = ap.parse_args()
     pkg = load_package()
     lib = pkg.load_library()
@@ -29,6 +30,14 @@ def main():
     tau = orc.random_fr(7, 1)[0]
     n = 1 << min(lmax, 23)
     x = orc.random_fr(2, n)
+    if args.dist == "witness":
+        rng = np.random.default_rng(3)
+        kind = rng.integers(0, 4, n)
+        small = np.zeros((n, 4), dtype=np.uint64)
+        small[:, 0] = rng.integers(1, 1 << 16, n)
+        small = orc.fr_op(5, small)  # canonical -> Montgomery
+        x[kind < 2] = 0
+        x[kind == 2] = small[kind == 2]
     for lg in ([] if args.no_msm else logs):
         # one context per size so that window size / precomputed tables are tuned for that size
         m = 1 << lg
@@ -39,8 +48,8 @@ def main():
         ms, out, bd = c.bench_msm(0, m, args.iters)
         ctx = c
         line = {"op": "msm", "log_n": lg, "ms": ms, "points_per_s": m / ms * 1e3, "breakdown_ms": bd,
-                "precomp": os.environ.get("ZP_MSM_PRECOMP", "1")}
-        if lg <= 14:
+                "precomp": os.environ.get("ZP_MSM_PRECOMP", "1"), "dist": args.dist}
+        if lg <= 16:
             srs = ctx.read_srs(m)
             line["matches_oracle"] = bool(np.array_equal(out, orc.msm(srs, x[:m].copy())))
         print(json.dumps(line), flush=True)
