@@ -160,10 +160,13 @@ def main():
     ctx.preprocess(sel, oc.tables())
     del sel
     if world > 1:
-        gather_in = torch.empty(192, dtype=torch.uint8, device="cuda")
-        gather_out = torch.empty(192 * world, dtype=torch.uint8, device="cuda")
+        gather_bufs = {}  # one 192-byte XYZZ partial sum per member of a commitment batch
 
         def allgather(data):
+            if len(data) not in gather_bufs:
+                gather_bufs[len(data)] = (torch.empty(len(data), dtype=torch.uint8, device="cuda"),
+                                          torch.empty(len(data) * world, dtype=torch.uint8, device="cuda"))
+            gather_in, gather_out = gather_bufs[len(data)]
             gather_in.copy_(torch.frombuffer(bytearray(data), dtype=torch.uint8))
             dist.all_gather_into_tensor(gather_out, gather_in)
             return bytes(gather_out.cpu().numpy())
@@ -213,8 +216,8 @@ def main():
     sampler.start()
     t0 = time.perf_counter()
     e0.record(stream)
-    acc_ms = acc_mads = 0.0
-    acc_launch = 0
+    acc_ms = acc_mads = exec_mads = 0.0
+    acc_launch = acc_commits = 0
     phase = {"ntt_ms": 0.0, "msm_ms": 0.0, "quotient_ms": 0.0, "other_ms": 0.0}
     for _ in range(args.steps):
         words = ctx.prove_resident().to_words()
@@ -222,6 +225,8 @@ def main():
         acc_ms += st["accumulate_ms"]
         acc_mads += st["algorithmic_mads"]
         acc_launch += st["launches"]
+        exec_mads += st["executed_mads"]
+        acc_commits += st["commitments"]
         tm = ctx.last_timing()
         for k in phase:
             phase[k] += tm[k] / args.steps
@@ -262,19 +267,26 @@ def main():
         return
 
     # ---- roofline of the dominant kernel (MSM bucket accumulation, integer-pipe bound) + the NTT (HBM)
-    achieved = acc_mads / (acc_ms * 1e-3) / 1e12 if acc_ms > 0 else None  # T mad/s
+    achieved = acc_mads / (acc_ms * 1e-3) / 1e12 if acc_ms > 0 else None  # T mad/s, SURVEY 8d count (XYZZ: 10 products / entry)
+    executed = exec_mads / (acc_ms * 1e-3) / 1e12 if acc_ms > 0 else None  # T mad/s actually issued (batch-affine: ~6.2 / entry)
     traffic = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
         if world == 1 and args.height == 15:
-            traffic = tj["msm_accumulate_kernel"]["traffic_bytes_per_launch"]  # bytes per launch, one ncu --set full capture
+            traffic = tj["ba_down0_kernel"]["traffic_bytes_per_launch"]  # bytes per launch, one ncu --set full capture
     except Exception:  # noqa: BLE001
         pass
-    roofline = {"bound": "int32-mad", "kernel": "msm_accumulate_kernel", "achieved": achieved, "peak": int_peak,
-                "unit": "Tmad/s", "frac": (achieved / int_peak) if achieved and int_peak else None, "traffic": traffic,
-                "traffic_unit": "bytes per launch (dram read + write, ncu)",
-                "peak_source": "in-run dependent-free mad.lo.u32 microbenchmark (SURVEY 8d); algorithmic ops = 10*588*M*W",
-                "launches": acc_launch, "avg_launch_ms": acc_ms / max(acc_launch, 1),
+    roofline = {"bound": "int32-mad",
+                "kernel": "MSM bucket accumulation: ba_up0_kernel + ba_down0_kernel (batch-affine rounds) + msm_accumulate_kernel",
+                "achieved": achieved, "peak": int_peak,
+                "unit": "Tmad/s", "frac": (achieved / int_peak) if achieved and int_peak else None,
+                "executed_achieved": executed, "executed_frac": (executed / int_peak) if executed and int_peak else None,
+                "traffic": traffic, "traffic_unit": "bytes per launch of ba_down0_kernel round 1 (dram read + write, ncu)",
+                "peak_source": "in-run dependent-free mad.lo.u32 microbenchmark (SURVEY 8d); achieved = algorithmic ops 10*588*M*W / "
+                               "device time of the stage; executed_* counts the multiply-adds really issued (a batch-affine "
+                               "addition is ~6.2 Fq products instead of the 10 of the XYZZ formula 8d assumes)",
+                "launches": acc_launch, "commitments": acc_commits, "avg_launch_ms": acc_ms / max(acc_launch, 1),
+                "avg_ms_per_commitment": acc_ms / max(acc_commits, 1),
                 "share_of_step": acc_ms / args.steps / step_ms}
     peaks = {}
     try:

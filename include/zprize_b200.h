@@ -153,7 +153,9 @@ int zp_prover_prove_resident(zp_prover* p, ProofC* out);
  * proof read out4 = { sum of kernel ms, launches, algorithmic 32-bit multiply-adds (10*588*M*W),
  * sum of all MSM kernel ms }. */
 int zp_prover_collect_msm_stats(zp_prover* p, int enable);
-int zp_prover_msm_stats(zp_prover* p, double* out4);
+/* out6: bucket-accumulation ms (batch-affine rounds + XYZZ accumulate), MSM pipelines launched, algorithmic mads
+ * (10*588*M*W), all MSM stages ms, mads actually issued (estimate), commitments produced */
+int zp_prover_msm_stats(zp_prover* p, double* out6);
 /* Multi-GPU sharding of the commitments (one process per GPU, every rank holds the same key and witness):
  * rank r computes each MSM over points [r*ceil(n/world), (r+1)*ceil(n/world)) only and the partial sums
  * are exchanged with `allgather(user, send, recv, bytes_per_rank)` — recv holds world * bytes_per_rank
@@ -215,8 +217,12 @@ int zp_bench_download(zp_prover* p, int slot, uint64_t* host, size_t n_fr);
 int zp_bench_ntt(zp_prover* p, int kind, int log_n, int slot_in, int slot_out, int iters, double* ms);
 /* runs `iters` MSMs of n points with scalars in `slot`; *ms = average device ms (host tail included) */
 int zp_bench_msm(zp_prover* p, int slot, size_t n, int iters, double* ms, uint64_t* out_affine);
-/* per-kernel device time of the last zp_bench_msm iteration: digits, scan, scatter, accumulate, reduce */
-int zp_bench_msm_breakdown(zp_prover* p, double* ms5);
+/* the same for `nbatch` (<= 8) scalar vectors over the same points in ONE pipeline (the batch the prover uses for
+ * independent commitments); *ms = average device ms per batch */
+int zp_bench_msm_batch(zp_prover* p, int slot, size_t n, int nbatch, int iters, double* ms, uint64_t* out_affine);
+/* per-stage device time of the last zp_bench_msm iteration: digits, scan, scatter, batch-affine rounds,
+ * accumulate (+ folds), reduce */
+int zp_bench_msm_breakdown(zp_prover* p, double* ms6);
 /* integer-pipe microbenchmark: mode 0 = IMAD (mad.lo), 1 = IMAD.WIDE (mad.wide), 2 = Fq Montgomery products,
  * 3 = Fq Montgomery squarings; returns giga-operations per second (instructions for 0/1, field operations for 2/3) */
 int zp_bench_int_pipe(zp_prover* p, int mode, double* gops);

@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--ntt", type=int, default=0)
     ap.add_argument("--no-msm", action="store_true", dest="no_msm")
+    ap.add_argument("--batch", type=int, default=1, help="scalar vectors per MSM pipeline (the prover batches independent commitments)")
     ap.add_argument("--dist", default="uniform", help="uniform | witness (50%% zeros, 25%% values < 2^16, 25%% uniform; SURVEY 8d config 3)")
     args = ap.parse_args()
     pkg = load_package()
@@ -45,9 +46,10 @@ def main():
         c.generate_srs(tau)
         c.bench_alloc(0, m)
         c.bench_upload(0, x[:m].copy())
-        ms, out, bd = c.bench_msm(0, m, args.iters)
+        ms, out, bd = c.bench_msm(0, m, args.iters, args.batch)
         ctx = c
-        line = {"op": "msm", "log_n": lg, "ms": ms, "points_per_s": m / ms * 1e3, "breakdown_ms": bd,
+        line = {"op": "msm", "log_n": lg, "batch": args.batch, "ms": ms, "ms_per_msm": ms / args.batch,
+                "points_per_s": m * args.batch / ms * 1e3, "breakdown_ms": bd, "ba_rounds": os.environ.get("ZP_MSM_BA_ROUNDS", "default"),
                 "precomp": os.environ.get("ZP_MSM_PRECOMP", "1"), "dist": args.dist}
         if lg <= 16:
             srs = ctx.read_srs(m)

@@ -24,7 +24,7 @@ int guard(F&& f) {
 }
 struct BenchState {
     DevBuf<fr_t> slot[8];
-    double msm_ms[5] = {0, 0, 0, 0, 0};
+    double msm_ms[6] = {0, 0, 0, 0, 0, 0};
 };
 std::map<zp_prover*, BenchState*> g_bench;
 BenchState& bench_of(zp_prover* p) {
@@ -100,13 +100,15 @@ int zp_prover_prove(zp_prover* p, const CircuitC* c, ProofC* out) { return guard
 int zp_prover_upload_witness(zp_prover* p, const CircuitC* c) { return guard([&] { P(p)->upload_witness(*c); }); }
 int zp_prover_prove_resident(zp_prover* p, ProofC* out) { return guard([&] { P(p)->prove_resident(out); }); }
 int zp_prover_collect_msm_stats(zp_prover* p, int enable) { return guard([&] { P(p)->collect_msm_stats = enable != 0; }); }
-int zp_prover_msm_stats(zp_prover* p, double* out4) {
+int zp_prover_msm_stats(zp_prover* p, double* out6) {
     return guard([&] {
         Prover* pr = P(p);
-        out4[0] = pr->msm_acc_ms;
-        out4[1] = pr->msm_launches;
-        out4[2] = pr->msm_mads;
-        out4[3] = pr->msm_all_ms;
+        out6[0] = pr->msm_acc_ms;
+        out6[1] = pr->msm_launches;
+        out6[2] = pr->msm_mads;
+        out6[3] = pr->msm_all_ms;
+        out6[4] = pr->msm_exec_mads;
+        out6[5] = pr->msm_count;
     });
 }
 int zp_prover_set_shard(zp_prover* p, int rank, int world, zp_allgather_fn fn, void* user) {
@@ -505,17 +507,23 @@ int zp_bench_ntt(zp_prover* p, int kind, int log_n, int slot_in, int slot_out, i
     });
 }
 int zp_bench_msm(zp_prover* p, int slot, size_t n, int iters, double* ms, uint64_t* out_affine) {
+    return zp_bench_msm_batch(p, slot, n, 1, iters, ms, out_affine);
+}
+int zp_bench_msm_batch(zp_prover* p, int slot, size_t n, int nbatch, int iters, double* ms, uint64_t* out_affine) {
     return guard([&] {
+        if (nbatch < 1 || nbatch > MSM_MAX_BATCH) throw std::runtime_error("zp_bench_msm_batch: batch size out of range");
         Prover* pr = P(p);
         BenchState& b = bench_of(p);
         if (b.slot[slot].n < n || pr->srs.n < n) throw std::runtime_error("zp_bench_msm: slot or SRS too small");
         cudaEvent_t e0, e1;
         ZP_CUDA(cudaEventCreate(&e0));
         ZP_CUDA(cudaEventCreate(&e1));
-        host::G1 r = pr->msm_over_srs(b.slot[slot].p, 0, n, pr->srs.n);  // warm-up (workspace / table allocation)
+        const fr_t* sp[MSM_MAX_BATCH];
+        for (int k = 0; k < nbatch; k++) sp[k] = b.slot[slot].p;  // the same scalars nbatch times: same work per member
+        host::G1 r = pr->msm_over_srs_batch(sp, nbatch, 0, n, pr->srs.n)[0];  // warm-up (workspace / table allocation)
         pr->MW.timing = true;
         ZP_CUDA(cudaEventRecord(e0, pr->st));
-        for (int i = 0; i < iters; i++) r = pr->msm_over_srs(b.slot[slot].p, 0, n, pr->srs.n);
+        for (int i = 0; i < iters; i++) r = pr->msm_over_srs_batch(sp, nbatch, 0, n, pr->srs.n)[nbatch - 1];
         ZP_CUDA(cudaEventRecord(e1, pr->st));
         ZP_CUDA(cudaEventSynchronize(e1));
         float t = 0;
@@ -523,14 +531,14 @@ int zp_bench_msm(zp_prover* p, int slot, size_t n, int iters, double* ms, uint64
         *ms = t / iters;
         if (out_affine) msm_to_affine_out(r, out_affine);
         pr->MW.timing = false;
-        for (int k = 0; k < 5; k++) b.msm_ms[k] = pr->MW.last_ms[k];
+        for (int k = 0; k < 6; k++) b.msm_ms[k] = pr->MW.last_ms[k];
         cudaEventDestroy(e0);
         cudaEventDestroy(e1);
     });
 }
-int zp_bench_msm_breakdown(zp_prover* p, double* ms5) {
+int zp_bench_msm_breakdown(zp_prover* p, double* ms6) {
     return guard([&] {
-        for (int k = 0; k < 5; k++) ms5[k] = bench_of(p).msm_ms[k];
+        for (int k = 0; k < 6; k++) ms6[k] = bench_of(p).msm_ms[k];
     });
 }
 

@@ -53,8 +53,8 @@ static int msm_reduce_groups(const MsmConfig& cfg) {
     return groups;
 }
 
-void MsmWorkspace::reserve(size_t n, const MsmConfig& cfg) {
-    size_t wn = (size_t)cfg.nwin * n, wb = (size_t)cfg.nsets * cfg.nbuckets;
+void MsmWorkspace::reserve(size_t n, const MsmConfig& cfg, int nbatch) {
+    size_t wn = (size_t)nbatch * cfg.nwin * n, wb = (size_t)nbatch * cfg.nsets * cfg.nbuckets;
     if (digits.n < wn) digits.alloc(wn);
     if (sorted.n < wn) sorted.alloc(wn);
     if (start.n < wb + 1) start.alloc(wb + 1);
@@ -73,23 +73,30 @@ void MsmWorkspace::reserve(size_t n, const MsmConfig& cfg) {
     }
     if (ba_rounds == 0) {
         const char* br = getenv("ZP_MSM_BA_ROUNDS");
-        ba_rounds = br ? atoi(br) : 0;  // opt-in: measured 25.3 -> 24.0 ms at 2^22 with 3 rounds (profiles/r01_msm_batch_affine.log)
+        // default 3 rounds: measured 25.3 -> 20.3 ms at 2^22 (profiles/r01b_msm_batch_affine.log); 0 disables
+        ba_rounds = br ? atoi(br) : 3;
+        ba_rounds_forced = br != nullptr;
         if (ba_rounds <= 0) ba_rounds = -1;  // disabled
         const char* bm = getenv("ZP_MSM_BA_MIN_LOG");
         if (bm) ba_min_entries = (size_t)1 << atoi(bm);
     }
     if (!counter.p) counter.alloc(1);
-    size_t np = (size_t)cfg.nsets * msm_reduce_groups(cfg);
+    size_t nsets = (size_t)nbatch * cfg.nsets;
+    size_t np = nsets * msm_reduce_groups(cfg);
     if (partial.n < np) partial.alloc(np);
-    if (final_sums.n < (size_t)cfg.nsets) final_sums.alloc(cfg.nsets);
-    if (np < (size_t)cfg.nsets) np = cfg.nsets;
+    if (final_sums.n < nsets) final_sums.alloc(nsets);
+    if (np < nsets) np = nsets;
     if (partial_host.size() < np) partial_host.resize(np);
 }
 
-__global__ void __launch_bounds__(256) msm_digits_kernel(const fr_t* __restrict__ scalars, size_t n, int c, int nwin, int nbuckets,
+// blockIdx.y = member of the batch (several scalar vectors over the same points, one bucket-set group each)
+__global__ void __launch_bounds__(256) msm_digits_kernel(MsmBatch batch, size_t n, int c, int nwin, int nbuckets,
                                                          int one_set, uint32_t* __restrict__ digits, uint32_t* __restrict__ hist) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const fr_t* __restrict__ scalars = batch.s[blockIdx.y];
+    digits += (size_t)blockIdx.y * nwin * n;
+    hist += (size_t)blockIdx.y * (one_set ? 1 : nwin) * nbuckets;
     fr_t s = load_fr(&scalars[i]).from_mont();
     uint32_t carry = 0;
     const uint32_t mask = (1u << c) - 1, half = 1u << (c - 1);
@@ -201,12 +208,13 @@ __global__ void __launch_bounds__(256) msm_scatter_kernel(const uint32_t* __rest
                                                           size_t tab_stride, uint32_t* __restrict__ cursor,
                                                           uint32_t* __restrict__ sorted) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int w = blockIdx.y;
+    const int w = blockIdx.y % nwin, b = blockIdx.y / nwin;  // window, batch member
     if (i >= n) return;
-    uint32_t dg = digits[(size_t)w * n + i];
+    uint32_t dg = digits[(size_t)blockIdx.y * n + i];
     uint32_t d = dg & 0x7fffffffu;
     if (!d) return;
-    uint32_t pos = atomicAdd(&cursor[(tab_stride ? 0 : (size_t)w * nbuckets) + d - 1], 1u);
+    const size_t set = tab_stride ? (size_t)b : (size_t)b * nwin + w;
+    uint32_t pos = atomicAdd(&cursor[set * nbuckets + d - 1], 1u);
     // with a precomputed table the entry addresses row w of the table: 2^(c w) * P_i
     sorted[pos] = (uint32_t)(tab_stride ? (size_t)w * tab_stride + i : i) | (dg & 0x80000000u);
 }
@@ -419,10 +427,13 @@ __global__ void __launch_bounds__(128) msm_final_kernel(const xyzz_t* __restrict
     if (threadIdx.x == 0) store_xyzz(&final_out[blockIdx.x], sm[0]);
 }
 
-static void msm_launch_impl(MsmWorkspace& ws, const MsmConfig& cfg, const affine_t* points, const fr_t* scalars, size_t n, bool allow_ba,
-                            cudaStream_t st) {
-    ws.reserve(n, cfg);
-    const size_t wb = (size_t)cfg.nsets * cfg.nbuckets, wn = (size_t)cfg.nwin * n;
+static void msm_launch_impl(MsmWorkspace& ws, const MsmConfig& cfg, const affine_t* points, const MsmBatch& batch, int nbatch, size_t n,
+                            bool allow_ba, cudaStream_t st) {
+    if (nbatch < 1 || nbatch > MSM_MAX_BATCH) throw std::runtime_error("msm: batch size out of range");
+    ws.reserve(n, cfg, nbatch);
+    const int nsets = nbatch * cfg.nsets;
+    const size_t wb = (size_t)nsets * cfg.nbuckets, wn = (size_t)nbatch * cfg.nwin * n;
+    if (wn >= ((size_t)1 << 31)) throw std::runtime_error("msm: batch too large for 31-bit entry indices");
     if (cfg.tab_stride && (size_t)cfg.nwin * cfg.tab_stride >= ((size_t)1 << 31))
         throw std::runtime_error("msm: precomputed table too large for 31-bit indices");
     auto mark = [&](int k) {
@@ -431,32 +442,39 @@ static void msm_launch_impl(MsmWorkspace& ws, const MsmConfig& cfg, const affine
         ZP_CUDA(cudaEventRecord(ws.ev[k], st));
     };
     ws.last_points = points;
-    ws.last_scalars = scalars;
+    ws.last_batch = batch;
+    ws.last_nbatch = nbatch;
     ws.last_n = n;
     ZP_CUDA(cudaMemsetAsync(ws.cursor.p, 0, wb * sizeof(uint32_t), st));
     mark(0);
     if (n) {
-        ZP_LAUNCH(msm_digits_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, scalars, n, cfg.c, cfg.nwin, cfg.nbuckets,
-                  cfg.tab_stride ? 1 : 0, ws.digits.p, ws.cursor.p);
+        ZP_LAUNCH(msm_digits_kernel, dim3((unsigned)((n + 255) / 256), nbatch), dim3(256), 0, st, batch, n, cfg.c, cfg.nwin,
+                  cfg.nbuckets, cfg.tab_stride ? 1 : 0, ws.digits.p, ws.cursor.p);
     }
     mark(1);
     msm_scan(ws.cursor.p, ws.start.p, wb, ws.tile_sum.p, st);
     mark(2);
     if (n) {
-        ZP_LAUNCH(msm_scatter_kernel, dim3((unsigned)((n + 255) / 256), cfg.nwin), dim3(256), 0, st, ws.digits.p, n, cfg.nwin,
+        ZP_LAUNCH(msm_scatter_kernel, dim3((unsigned)((n + 255) / 256), cfg.nwin * nbatch), dim3(256), 0, st, ws.digits.p, n, cfg.nwin,
                   cfg.nbuckets, cfg.tab_stride, ws.cursor.p, ws.sorted.p);
     }
+    mark(3);
     // ---- batch-affine pre-reduction rounds
     const uint32_t *run_begin = ws.start.p, *run_end = ws.cursor.p, *entries = ws.sorted.p;
     const affine_t* pts = points;
     size_t est = wn;  // upper bound on the bucket entries still to be added
     int rounds = (allow_ba && wn >= ws.ba_min_entries) ? ws.ba_rounds : 0;
+    // leave >= 8 entries per bucket on average for the XYZZ pass (each round has a fixed cost of ~0.7 ms)
+    if (!ws.ba_rounds_forced)
+        while (rounds > 0 && ((wn / wb) >> rounds) < 8) rounds--;
     ws.ba_used = rounds > 0;
     if (rounds > 0) {
         size_t cap0 = wn / 2 + wb;
+        size_t up0 = (cap0 / (BA_K * BA_T) + 1) * BA_T;  // leaf groups (level-1 nodes of the inversion tree)
         if (ws.ba_pts[0].n < cap0) ws.ba_pts[0].alloc(cap0);
         if (rounds > 1 && ws.ba_pts[1].n < cap0 / 2 + wb) ws.ba_pts[1].alloc(cap0 / 2 + wb);
-        if (ws.ba_den.n < cap0 + cap0 / (BI_CH - 1) + 64) ws.ba_den.alloc(cap0 + cap0 / (BI_CH - 1) + 64);
+        if (ws.ba_pre.n < cap0) ws.ba_pre.alloc(cap0);
+        if (ws.ba_den.n < up0 + up0 / (BI_CH - 1) + 64) ws.ba_den.alloc(up0 + up0 / (BI_CH - 1) + 64);
         if (ws.ba_src.n < cap0) ws.ba_src.alloc(cap0);
         if (ws.ba_cnt.n < wb) ws.ba_cnt.alloc(wb);
         for (int k = 0; k < 2; k++)
@@ -467,12 +485,16 @@ static void msm_launch_impl(MsmWorkspace& ws, const MsmConfig& cfg, const affine
             size_t cap = est / 2 + wb;
             uint32_t* rs = ws.ba_rs[r & 1].p;
             affine_t* out = ws.ba_pts[r & 1].p;
+            unsigned nblk = (unsigned)((cap + BA_K * BA_T - 1) / (BA_K * BA_T));
+            size_t m = (size_t)nblk * BA_T;
             ZP_LAUNCH(ba_pair_count_kernel, dim3((unsigned)((wb + 255) / 256)), dim3(256), 0, st, run_begin, run_end, wb, ws.ba_cnt.p);
             msm_scan(ws.ba_cnt.p, rs, wb, ws.tile_sum.p, st);
-            ZP_LAUNCH(ba_pair_denoms_kernel, dim3((unsigned)((cap + 255) / 256)), dim3(256), 0, st, run_begin, run_end, rs, wb, cap,
-                      entries, pts, ws.ba_den.p, ws.ba_src.p, ws.ba_flag.p);
-            fq_batch_inverse(ws.ba_den.p, cap, ws.ba_den.p + cap, st);
-            ZP_LAUNCH(ba_pair_sums_kernel, dim3((unsigned)((cap + 255) / 256)), dim3(256), 0, st, ws.ba_src.p, cap, entries, pts,
+            ZP_LAUNCH(ba_slots_kernel, dim3((unsigned)((wb * 32 + 255) / 256)), dim3(256), 0, st, run_begin, run_end, rs, wb,
+                      ws.ba_src.p);
+            ZP_LAUNCH(ba_up0_kernel, dim3(nblk), dim3(BA_T), 0, st, ws.ba_src.p, rs + wb, cap, entries, pts, ws.ba_pre.p,
+                      ws.ba_den.p, ws.ba_flag.p);
+            fq_batch_inverse(ws.ba_den.p, m, ws.ba_den.p + m, st);
+            ZP_LAUNCH(ba_down0_kernel, dim3(nblk), dim3(BA_T), 0, st, ws.ba_src.p, rs + wb, cap, entries, pts, ws.ba_pre.p,
                       ws.ba_den.p, out);
             run_begin = rs;
             run_end = rs + 1;
@@ -501,7 +523,7 @@ static void msm_launch_impl(MsmWorkspace& ws, const MsmConfig& cfg, const affine
     msm_scan(ws.seg_cnt.p, ws.seg_start.p, wb, ws.tile_sum.p, st);
     ZP_LAUNCH(msm_segdesc_kernel, dim3((unsigned)((wb + 255) / 256)), dim3(256), 0, st, run_begin, run_end, ws.seg_start.p, wb,
               (uint32_t)ws.seg, ws.desc.p);
-    mark(3);
+    mark(4);
     {
         ZP_CUDA(cudaMemsetAsync(ws.counter.p, 0, sizeof(uint32_t), st));
         int variant = ws.acc_variant;
@@ -520,56 +542,70 @@ static void msm_launch_impl(MsmWorkspace& ws, const MsmConfig& cfg, const affine
     }
     ZP_LAUNCH(msm_fold_small_kernel, dim3((unsigned)((wb + 127) / 128)), dim3(128), 0, st, ws.segs.p, ws.seg_start.p, wb);
     ZP_LAUNCH(msm_fold_kernel, dim3((unsigned)((wb + 3) / 4)), dim3(128), 0, st, ws.segs.p, ws.seg_start.p, wb);
-    mark(4);
+    mark(5);
     int groups = msm_reduce_groups(cfg);
     int bg = cfg.nbuckets / groups;
     int T = bg < 128 ? bg : 128;
-    ZP_LAUNCH(msm_reduce_kernel, dim3(cfg.nsets * groups), dim3(T), (size_t)T * sizeof(xyzz_t), st, ws.segs.p, ws.seg_start.p,
+    ZP_LAUNCH(msm_reduce_kernel, dim3(nsets * groups), dim3(T), (size_t)T * sizeof(xyzz_t), st, ws.segs.p, ws.seg_start.p,
               cfg.nbuckets, groups, ws.partial.p);
-    ZP_LAUNCH(msm_final_kernel, dim3(cfg.nsets), dim3(128), 0, st, ws.partial.p, groups, ws.final_sums.p);
-    mark(5);
-    ZP_CUDA(cudaMemcpyAsync(ws.partial_host.data(), ws.final_sums.p, (size_t)cfg.nsets * sizeof(xyzz_t),
-                            cudaMemcpyDeviceToHost, st));
+    ZP_LAUNCH(msm_final_kernel, dim3(nsets), dim3(128), 0, st, ws.partial.p, groups, ws.final_sums.p);
+    mark(6);
+    ZP_CUDA(cudaMemcpyAsync(ws.partial_host.data(), ws.final_sums.p, (size_t)nsets * sizeof(xyzz_t), cudaMemcpyDeviceToHost, st));
     if (ws.ba_used) {
         // entries the accumulate kernel saw (for the roofline accounting) + the degenerate-pair flag
         ZP_CUDA(cudaMemcpyAsync(&ws.ba_flag_host[1], run_begin + wb, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         ZP_CUDA(cudaMemcpyAsync(&ws.ba_flag_host[0], ws.ba_flag.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     }
     ws.acc_entries = (double)wn;
+    ws.ba_rounds_used = rounds > 0 ? rounds : 0;
 }
 
 void msm_launch(MsmWorkspace& ws, const MsmConfig& cfg, const affine_t* points, const fr_t* scalars, size_t n, cudaStream_t st) {
-    msm_launch_impl(ws, cfg, points, scalars, n, true, st);
+    MsmBatch b{};
+    b.s[0] = scalars;
+    msm_launch_impl(ws, cfg, points, b, 1, n, true, st);
+}
+void msm_launch_batch(MsmWorkspace& ws, const MsmConfig& cfg, const affine_t* points, const fr_t* const* scalars, int nbatch, size_t n,
+                      cudaStream_t st) {
+    MsmBatch b{};
+    for (int k = 0; k < nbatch && k < MSM_MAX_BATCH; k++) b.s[k] = scalars[k];
+    msm_launch_impl(ws, cfg, points, b, nbatch, n, true, st);
 }
 
-host::G1 msm_collect(MsmWorkspace& ws, const MsmConfig& cfg, cudaStream_t st) {
+std::vector<host::G1> msm_collect_batch(MsmWorkspace& ws, const MsmConfig& cfg, cudaStream_t st) {
     ZP_CUDA(cudaStreamSynchronize(st));
     if (ws.ba_used) {
         if (ws.ba_flag_host[0]) {
             // a pair with equal x-coordinates: redo this MSM on the exact XYZZ-only path
-            msm_launch_impl(ws, cfg, ws.last_points, ws.last_scalars, ws.last_n, false, st);
+            msm_launch_impl(ws, cfg, ws.last_points, ws.last_batch, ws.last_nbatch, ws.last_n, false, st);
             ZP_CUDA(cudaStreamSynchronize(st));
         } else {
             ws.acc_entries = (double)ws.ba_flag_host[1];
         }
     }
-    if (ws.timing && ws.ev[5]) {
-        for (int k = 0; k < 5; k++) {
+    if (ws.timing && ws.ev[6]) {
+        for (int k = 0; k < 6; k++) {
             float ms = 0;
             ZP_CUDA(cudaEventElapsedTime(&ms, ws.ev[k], ws.ev[k + 1]));
             ws.last_ms[k] = ms;
         }
     }
-    host::G1 total = host::G1::infinity();
-    if (cfg.nsets == 1) {
-        total = host::G1::from_dev(ws.partial_host[0]);  // precomputed tables: window weights are in the points
-    } else {
-        for (int w = cfg.nwin - 1; w >= 0; w--) {
-            for (int b = 0; b < cfg.c; b++) total.dbl_inplace();
-            total.add(host::G1::from_dev(ws.partial_host[w]));
+    std::vector<host::G1> res(ws.last_nbatch);
+    for (int b = 0; b < ws.last_nbatch; b++) {
+        const xyzz_t* ph = ws.partial_host.data() + (size_t)b * cfg.nsets;
+        host::G1 total = host::G1::infinity();
+        if (cfg.nsets == 1) {
+            total = host::G1::from_dev(ph[0]);  // precomputed tables: window weights are in the points
+        } else {
+            for (int w = cfg.nwin - 1; w >= 0; w--) {
+                for (int k = 0; k < cfg.c; k++) total.dbl_inplace();
+                total.add(host::G1::from_dev(ph[w]));
+            }
         }
+        res[b] = total;
     }
-    return total;
+    return res;
 }
+host::G1 msm_collect(MsmWorkspace& ws, const MsmConfig& cfg, cudaStream_t st) { return msm_collect_batch(ws, cfg, st)[0]; }
 
 }  // namespace zp

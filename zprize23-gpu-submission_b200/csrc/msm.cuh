@@ -24,6 +24,13 @@ MsmConfig msm_config_precomp(size_t n, size_t tab_stride);
 // dst[w * n + i] = 2^(c w) * src[i], w < nwin (dst may be larger than 4 GiB; built once per SRS)
 void msm_build_table(affine_t* dst, const affine_t* src, size_t n, int c, int nwin, cudaStream_t st);
 
+// Several scalar vectors over the same points go through ONE pipeline (one bucket-set group per member): the
+// latency-bound stages (scans, inversion-tree tops, bucket reduction) are paid once per batch instead of once per MSM.
+static const int MSM_MAX_BATCH = 8;
+struct MsmBatch {
+    const fr_t* s[MSM_MAX_BATCH];
+};
+
 struct MsmWorkspace {
     DevBuf<uint32_t> digits;   // [nwin][n]   |d| | sign << 31
     DevBuf<uint32_t> sorted;   // [<= nwin*n] point index | sign << 31, grouped by (window, bucket)
@@ -38,10 +45,12 @@ struct MsmWorkspace {
     int sm_count = 0;
     int acc_variant = 3;       // resident CTAs per SM of the accumulate kernel (ZP_ACC_VARIANT=3|4|5)
     // batch-affine pre-reduction (msm_affine.cuh): rounds of pairwise affine additions before the XYZZ accumulation
-    int ba_rounds = 0;            // 0 = not read yet, -1 = off (default), > 0 = rounds (ZP_MSM_BA_ROUNDS)
+    int ba_rounds = 0;            // 0 = not read yet, -1 = off, > 0 = rounds (ZP_MSM_BA_ROUNDS, default 3)
+    bool ba_rounds_forced = false;// set by the environment: do not adapt the round count to the bucket load
     size_t ba_min_entries = (size_t)1 << 22;
     DevBuf<affine_t> ba_pts[2];   // materialised partial sums (ping-pong)
-    DevBuf<fq_t> ba_den;          // denominators -> inverses, followed by the product-tree levels
+    DevBuf<fq_t> ba_pre;          // per-slot prefix products of the leaf groups of the inversion tree
+    DevBuf<fq_t> ba_den;          // leaf-group products -> inverses, followed by the upper product-tree levels
     DevBuf<uint32_t> ba_src;      // source index of each output slot
     DevBuf<uint32_t> ba_cnt, ba_rs[2];
     DevBuf<uint32_t> ba_flag;     // [0] degenerate pair seen, [1] entries left for the accumulation
@@ -50,18 +59,20 @@ struct MsmWorkspace {
     double acc_entries = 0;       // bucket entries the accumulate kernel of the last launch processed
     // arguments of the last launch (to redo it on the plain path if a degenerate pair was seen)
     const affine_t* last_points = nullptr;
-    const fr_t* last_scalars = nullptr;
+    MsmBatch last_batch{};
+    int last_nbatch = 1;
     size_t last_n = 0;
+    int ba_rounds_used = 0;    // batch-affine rounds of the last launch
     size_t seg = 0;            // points per work segment (2x the mean bucket load, >= 32)
     size_t max_segs = 0;
     DevBuf<xyzz_t> partial;    // [nwin * MSM_REDUCE_GROUPS]
     DevBuf<xyzz_t> final_sums; // [nsets] per-set sums (what returns to the host)
     std::vector<xyzz_t> partial_host;
-    // optional per-kernel timing (bench only): digits, scan, scatter, accumulate, reduce
+    // optional per-stage timing (bench only): digits, scan, scatter, batch-affine rounds, accumulate (+ folds), reduce
     bool timing = false;
-    cudaEvent_t ev[6] = {0, 0, 0, 0, 0, 0};
-    double last_ms[5] = {0, 0, 0, 0, 0};
-    void reserve(size_t n, const MsmConfig& cfg);
+    cudaEvent_t ev[7] = {0, 0, 0, 0, 0, 0, 0};
+    double last_ms[6] = {0, 0, 0, 0, 0, 0};
+    void reserve(size_t n, const MsmConfig& cfg, int nbatch = 1);
 };
 static const int MSM_REDUCE_GROUPS = 8;
 
@@ -72,5 +83,9 @@ static const int MSM_REDUCE_GROUPS = 8;
 void msm_launch(MsmWorkspace& ws, const MsmConfig& cfg, const affine_t* points, const fr_t* scalars, size_t n,
                 cudaStream_t st);
 host::G1 msm_collect(MsmWorkspace& ws, const MsmConfig& cfg, cudaStream_t st);
+// batch of <= MSM_MAX_BATCH scalar vectors (device pointers, n each) over the same points; one result per member
+void msm_launch_batch(MsmWorkspace& ws, const MsmConfig& cfg, const affine_t* points, const fr_t* const* scalars, int nbatch, size_t n,
+                      cudaStream_t st);
+std::vector<host::G1> msm_collect_batch(MsmWorkspace& ws, const MsmConfig& cfg, cudaStream_t st);
 
 }  // namespace zp

@@ -2,8 +2,9 @@
 //
 // Before the XYZZ accumulation, the points of every bucket run are added PAIRWISE in affine coordinates:
 //     lambda = (y2 - y1) / (x2 - x1),  x3 = lambda^2 - x1 - x2,  y3 = lambda (x1 - x3) - y1        (2M + 1S + 1 inversion)
-// with all inversions of a round shared through one parallel Montgomery batch inversion (3.4 products per element), i.e.
-// ~6.5 Fq products per addition instead of the 10 of an XYZZ mixed addition.  Each round halves the run lengths and
+// with all inversions of a round shared through one parallel Montgomery batch inversion (3 products per element: the
+// leaf level is fused with the denominators on the way up and with the additions on the way down), i.e. ~6 Fq products
+// per addition instead of the 10 of an XYZZ mixed addition.  Each round halves the run lengths and
 // materialises the partial sums contiguously, so later rounds and the final accumulation read sequential memory instead
 // of gathering from the SRS table.  A pair with x1 == x2 (P + P or P - P; impossible for distinct SRS powers, reachable
 // with repeated input points) raises a flag and the whole MSM is redone on the plain XYZZ path, so the result is exact
@@ -22,69 +23,99 @@ __global__ void __launch_bounds__(256) ba_pair_count_kernel(const uint32_t* __re
     cnt[b] = (len + 1) >> 1;
 }
 
-// bucket b with rs[b] <= j < rs[b+1]
-ZP_D size_t ba_find_bucket(const uint32_t* __restrict__ rs, size_t nb, uint32_t j) {
-    size_t lo = 0, hi = nb;
-    while (hi - lo > 1) {
-        size_t mid = (lo + hi) >> 1;
-        if (rs[mid] <= j) lo = mid; else hi = mid;
-    }
-    return lo;
+// Slot table: src0[j] = (index of the first point of pair j) << 1 | (the slot is a real pair, not a leftover).
+// One warp per bucket run, lanes over the pairs of the run (coalesced stores; no per-slot search).
+__global__ void __launch_bounds__(256) ba_slots_kernel(const uint32_t* __restrict__ begin, const uint32_t* __restrict__ endp,
+                                                       const uint32_t* __restrict__ rs, size_t nb, uint32_t* __restrict__ src0) {
+    size_t b = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (b >= nb) return;
+    const uint32_t b0 = begin[b], len = endp[b] - b0, o = rs[b], np = (len + 1) >> 1;
+    for (uint32_t t = lane; t < np; t += 32) src0[o + t] = ((b0 + 2 * t) << 1) | (2 * t + 1 < len ? 1u : 0u);
 }
 
-// den[j] = x2 - x1 of the j-th output slot (1 for an unpaired leftover or an unused slot); remembers the source index
-__global__ void __launch_bounds__(256) ba_pair_denoms_kernel(const uint32_t* __restrict__ begin, const uint32_t* __restrict__ endp,
-                                                             const uint32_t* __restrict__ rs, size_t nb, size_t cap,
-                                                             const uint32_t* __restrict__ entries, const affine_t* __restrict__ pts,
-                                                             fq_t* __restrict__ den, uint32_t* __restrict__ src0,
-                                                             uint32_t* __restrict__ flag) {
-    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= cap) return;
-    fq_t d = fq_t::one();
-    uint32_t s = 0xffffffffu;  // unused slot
-    if (j < rs[nb]) {
-        size_t b = ba_find_bucket(rs, nb, (uint32_t)j);
-        uint32_t t = (uint32_t)j - rs[b], len = endp[b] - begin[b];
-        uint32_t i0 = begin[b] + 2 * t;
-        s = i0 << 1;  // bit 0: this slot is a real pair
-        if (2 * t + 1 < len) {
-            s |= 1u;
-            uint32_t e0 = entries ? entries[i0] & 0x7fffffffu : i0, e1 = entries ? entries[i0 + 1] & 0x7fffffffu : i0 + 1;
-            d = load_fq(&pts[e1].x) - load_fq(&pts[e0].x);
-            if (d.is_zero()) {
-                *flag = 1;
-                d = fq_t::one();
+// A CTA of BA_T threads covers BA_K * BA_T consecutive slots; thread tl owns slots base + k * BA_T + tl (k < BA_K), so
+// every per-slot array is read and written coalesced.  Those BA_K slots form one leaf group of the inversion tree.
+static const int BA_K = 8;
+static const int BA_T = 256;
+
+// Leaf level of the batch inversion fused with the denominators den = x2 - x1 (1 for a leftover / unused / degenerate
+// slot): pre[j] = product of the group's denominators before slot j (k >= 1), up[group] = product of all BA_K.
+// The denominators themselves are not stored: the downward kernel reloads both points anyway.
+__global__ void __launch_bounds__(BA_T) ba_up0_kernel(const uint32_t* __restrict__ src0, const uint32_t* __restrict__ total_ptr,
+                                                      size_t cap, const uint32_t* __restrict__ entries,
+                                                      const affine_t* __restrict__ pts, fq_t* __restrict__ pre,
+                                                      fq_t* __restrict__ up, uint32_t* __restrict__ flag) {
+    const size_t base = (size_t)blockIdx.x * (BA_K * BA_T) + threadIdx.x;
+    const size_t total = *total_ptr;
+    fq_t acc = fq_t::one();
+#pragma unroll 1
+    for (int k = 0; k < BA_K; k++) {
+        const size_t j = base + (size_t)k * BA_T;
+        if (j >= cap) break;
+        bool pair = false;
+        fq_t d;
+        if (j < total) {
+            const uint32_t s = src0[j];
+            if (s & 1u) {
+                const uint32_t i0 = s >> 1;
+                const uint32_t e0 = entries ? entries[i0] & 0x7fffffffu : i0, e1 = entries ? entries[i0 + 1] & 0x7fffffffu : i0 + 1;
+                d = load_fq(&pts[e1].x) - load_fq(&pts[e0].x);
+                pair = true;
+                if (d.is_zero()) {
+                    *flag = 1;
+                    pair = false;
+                }
             }
         }
+        if (!pair) d = fq_t::one();
+        if (k) store_fq(&pre[j], acc);
+        if (k == 0) acc = d;
+        else if (pair) acc = acc * d;
     }
-    store_fq(&den[j], d);
-    src0[j] = s;
+    store_fq(&up[(size_t)blockIdx.x * BA_T + threadIdx.x], acc);
 }
 
-// out[j] = P(i0) + P(i0 + 1) using inv[j] = 1 / (x2 - x1), or a copy of the leftover point
-__global__ void __launch_bounds__(256) ba_pair_sums_kernel(const uint32_t* __restrict__ src0, size_t cap,
-                                                           const uint32_t* __restrict__ entries, const affine_t* __restrict__ pts,
-                                                           const fq_t* __restrict__ inv, affine_t* __restrict__ out) {
-    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= cap) return;
-    uint32_t s = src0[j];
-    if (s == 0xffffffffu) return;
-    uint32_t i0 = s >> 1;
-    uint32_t e0 = entries ? entries[i0] : i0;
-    fq_t x1 = load_fq(&pts[e0 & 0x7fffffffu].x), y1 = load_fq(&pts[e0 & 0x7fffffffu].y);
-    if (entries && (e0 >> 31)) y1 = y1.neg();
-    if (s & 1u) {
-        uint32_t e1 = entries ? entries[i0 + 1] : i0 + 1;
-        fq_t x2 = load_fq(&pts[e1 & 0x7fffffffu].x), y2 = load_fq(&pts[e1 & 0x7fffffffu].y);
-        if (entries && (e1 >> 31)) y2 = y2.neg();
-        fq_t lam = (y2 - y1) * load_fq(&inv[j]);
-        fq_t x3 = lam.sqr() - x1 - x2;
-        fq_t y3 = lam * (x1 - x3) - y1;
-        x1 = x3;
-        y1 = y3;
+// Leaf level downwards fused with the additions: from inv = 1 / (product of the group) recover each 1 / den[j]
+// (2 products per slot with the stored prefix products) and emit out[j] = P(i0) + P(i0 + 1), or the leftover point.
+__global__ void __launch_bounds__(BA_T, 2) ba_down0_kernel(const uint32_t* __restrict__ src0, const uint32_t* __restrict__ total_ptr,
+                                                        size_t cap, const uint32_t* __restrict__ entries,
+                                                        const affine_t* __restrict__ pts, const fq_t* __restrict__ pre,
+                                                        const fq_t* __restrict__ up_inv,
+                                                        affine_t* __restrict__ out) {
+    const size_t base = (size_t)blockIdx.x * (BA_K * BA_T) + threadIdx.x;
+    const size_t total = *total_ptr;
+    if (base >= total) return;  // slots of one thread ascend with k: nothing to emit
+    fq_t inv = load_fq(&up_inv[(size_t)blockIdx.x * BA_T + threadIdx.x]);
+#pragma unroll 1
+    for (int k = BA_K - 1; k >= 0; k--) {
+        const size_t j = base + (size_t)k * BA_T;
+        if (j >= total) continue;  // unused slots carry den = 1: inv is unchanged
+        const uint32_t s = src0[j];
+        const uint32_t i0 = s >> 1;
+        const uint32_t e0 = entries ? entries[i0] : i0;
+        fq_t x1 = load_fq(&pts[e0 & 0x7fffffffu].x), y1 = load_fq(&pts[e0 & 0x7fffffffu].y);
+        if (entries && (e0 >> 31)) y1 = y1.neg();
+        if (s & 1u) {
+            const uint32_t e1 = entries ? entries[i0 + 1] : i0 + 1;
+            fq_t x2 = load_fq(&pts[e1 & 0x7fffffffu].x), y2 = load_fq(&pts[e1 & 0x7fffffffu].y);
+            if (entries && (e1 >> 31)) y2 = y2.neg();
+            fq_t d = x2 - x1;
+            if (!d.is_zero()) {  // a degenerate pair was given den = 1 (the whole MSM is redone anyway)
+                fq_t ik = inv;
+                if (k) {
+                    ik = inv * load_fq(&pre[j]);
+                    inv = inv * d;
+                }
+                fq_t lam = (y2 - y1) * ik;
+                fq_t x3 = lam.sqr() - x1 - x2;
+                y1 = lam * (x1 - x3) - y1;
+                x1 = x3;
+            }
+        }
+        store_fq(&out[j].x, x1);
+        store_fq(&out[j].y, y1);
     }
-    store_fq(&out[j].x, x1);
-    store_fq(&out[j].y, y1);
 }
 
 // ---- parallel Montgomery batch inversion over a product tree with BI_CH children per node

@@ -105,6 +105,7 @@ void Prover::ensure_work_buffers(bool lookup) {
     need(lin, n);
     need(comb, n);
     need(wit, n);
+    need(wit2, n);
     if (lookup) {
         need(z28, n8);
         need(t_ev, n); need(f_ev, n); need(h1_ev, n); need(h2_ev, n);
@@ -294,6 +295,10 @@ void Prover::finish_pk() {
 // sum_{i in [lo, hi)} scalars[i - lo] * srs[i]; large ranges go through the precomputed window table of the
 // slice [lo, lo + slice) (built on first use; 13 x 384 MiB at N = 2^22)
 host::G1 Prover::msm_over_srs(const fr_t* scalars_dev, size_t lo, size_t hi, size_t slice) {
+    return msm_over_srs_batch(&scalars_dev, 1, lo, hi, slice)[0];
+}
+// the same for k scalar vectors at once (one MSM pipeline, see MsmBatch)
+std::vector<host::G1> Prover::msm_over_srs_batch(const fr_t* const* scalars_dev, int k, size_t lo, size_t hi, size_t slice) {
     MsmConfig cfg = msm_config_for(hi - lo);
     const affine_t* base = srs.p + lo;
     if (use_precomp && hi - lo >= precomp_min) {
@@ -308,45 +313,72 @@ host::G1 Prover::msm_over_srs(const fr_t* scalars_dev, size_t lo, size_t hi, siz
         cfg = tab_cfg;
         base = srs_tab.p;
     }
-    msm_launch(MW, cfg, base, scalars_dev, hi - lo, st);
-    host::G1 r = msm_collect(MW, cfg, st);
+    msm_launch_batch(MW, cfg, base, scalars_dev, k, hi - lo, st);
+    std::vector<host::G1> r = msm_collect_batch(MW, cfg, st);
     if (MW.timing) {
-        msm_acc_ms += MW.last_ms[3];
-        for (int k = 0; k < 5; k++) msm_all_ms += MW.last_ms[k];
-        msm_mads += 10.0 * 588.0 * (double)(hi - lo) * cfg.nwin;  // 10 * 588 * M * W
+        msm_acc_ms += MW.last_ms[3] + MW.last_ms[4];  // bucket accumulation: batch-affine rounds + XYZZ accumulate + folds
+        for (int i = 0; i < 6; i++) msm_all_ms += MW.last_ms[i];
+        double entries = (double)(hi - lo) * cfg.nwin * k;
+        msm_mads += 10.0 * 588.0 * entries;  // 10 * 588 * M * W
+        // multiply-adds actually issued: a batch-affine addition costs ~6.2 Fq products (3 for the shared inversion incl.
+        // the tree levels above the leaves, 3 for the chord), an XYZZ mixed addition 10
+        double left = MW.ba_used ? MW.acc_entries : entries;
+        msm_exec_mads += 588.0 * (6.2 * (entries - left) + 10.0 * left);
         msm_launches++;
+        msm_count += k;
     }
     return r;
 }
 
 void Prover::commit(const fr_t* coeffs_dev, size_t ncoef, CommitmentC* out, Fq* ox, Fq* oy, bool* oinf) {
-    Scope sc(CAT_MSM);
-    if (!srs.p) throw std::runtime_error("commit: no SRS loaded");
+    CommitmentC* outs[1] = {out};
     Fq x, y;
     bool inf;
-    if (!coeffs_dev || ncoef == 0) {
-        host::G1::infinity().to_affine(x, y, inf);
-    } else {
-        // point-range shard of this rank (the whole range when world == 1)
-        size_t chunk = (ncoef + shard_world - 1) / shard_world;
-        size_t lo = std::min(ncoef, (size_t)shard_rank * chunk), hi = std::min(ncoef, lo + chunk);
-        host::G1 r = host::G1::infinity();
-        if (hi > lo) r = msm_over_srs(coeffs_dev + lo, lo, hi, std::min(chunk, srs.n - lo));
-        if (shard_world > 1) {
-            if (!allgather) throw std::runtime_error("commit: sharded prover without an all-gather callback");
-            std::vector<host::G1> all(shard_world);
-            if (allgather(allgather_user, &r, all.data(), sizeof(host::G1)) != 0)
-                throw std::runtime_error("commit: all-gather of MSM partial sums failed");
-            r = host::G1::infinity();
-            for (int k = 0; k < shard_world; k++) r.add(all[k]);
-        }
-        r.to_affine(x, y, inf);
-    }
-    memcpy(out->x, x.v, 48);
-    memcpy(out->y, y.v, 48);
+    commit_batch(&coeffs_dev, 1, ncoef, outs, &x, &y, &inf);
     if (ox) *ox = x;
     if (oy) *oy = y;
     if (oinf) *oinf = inf;
+}
+
+// Commitments to k polynomials of ncoef coefficients each (null pointer / ncoef == 0: the identity).  The MSMs of the
+// non-trivial members run as ONE batch; when sharded, the k partial sums of a rank travel in one all-gather.
+void Prover::commit_batch(const fr_t* const* coeffs_dev, int k, size_t ncoef, CommitmentC* const* outs, Fq* xs, Fq* ys, bool* infs) {
+    Scope sc(CAT_MSM);
+    if (!srs.p) throw std::runtime_error("commit: no SRS loaded");
+    if (k < 1 || k > MSM_MAX_BATCH) throw std::runtime_error("commit_batch: batch size out of range");
+    std::vector<host::G1> res(k, host::G1::infinity());
+    std::vector<int> live;
+    for (int i = 0; i < k; i++)
+        if (coeffs_dev[i] && ncoef) live.push_back(i);
+    if (!live.empty()) {
+        // point-range shard of this rank (the whole range when world == 1)
+        size_t chunk = (ncoef + shard_world - 1) / shard_world;
+        size_t lo = std::min(ncoef, (size_t)shard_rank * chunk), hi = std::min(ncoef, lo + chunk);
+        const int m = (int)live.size();
+        std::vector<host::G1> part(m, host::G1::infinity());
+        if (hi > lo) {
+            std::vector<const fr_t*> sp(m);
+            for (int j = 0; j < m; j++) sp[j] = coeffs_dev[live[j]] + lo;
+            part = msm_over_srs_batch(sp.data(), m, lo, hi, std::min(chunk, srs.n - lo));
+        }
+        if (shard_world > 1) {
+            if (!allgather) throw std::runtime_error("commit: sharded prover without an all-gather callback");
+            std::vector<host::G1> all((size_t)shard_world * m);
+            if (allgather(allgather_user, part.data(), all.data(), sizeof(host::G1) * m) != 0)
+                throw std::runtime_error("commit: all-gather of MSM partial sums failed");
+            for (int j = 0; j < m; j++) {
+                host::G1 r = host::G1::infinity();
+                for (int w = 0; w < shard_world; w++) r.add(all[(size_t)w * m + j]);
+                part[j] = r;
+            }
+        }
+        for (int j = 0; j < m; j++) res[live[j]] = part[j];
+    }
+    for (int i = 0; i < k; i++) {
+        res[i].to_affine(xs[i], ys[i], infs[i]);
+        memcpy(outs[i]->x, xs[i].v, 48);
+        memcpy(outs[i]->y, ys[i].v, 48);
+    }
 }
 
 void Prover::verifier_key(uint64_t* out23) {
@@ -400,8 +432,8 @@ void Prover::prove_resident(ProofC* out) {
     memset(out, 0, sizeof(ProofC));
     const size_t cn = wit_n;
     const bool lookup_on = wit_lookup_on;
-    msm_acc_ms = msm_all_ms = msm_mads = 0;
-    msm_launches = 0;
+    msm_acc_ms = msm_all_ms = msm_mads = msm_exec_mads = 0;
+    msm_launches = msm_count = 0;
     MW.timing = collect_msm_stats;
     struct TimingOff { MsmWorkspace& w; ~TimingOff() { w.timing = false; } } timing_off{MW};
 
@@ -414,11 +446,18 @@ void Prover::prove_resident(ProofC* out) {
     // ---- 1. witness polynomials (prover.rs:192-228)
     CommitmentC* comm = &out->a_comm;  // 19 consecutive CommitmentC
     static const char* wl[4] = {"w_l", "w_r", "w_o", "w_4"};
-    for (int k = 0; k < 4; k++) {
-        { Scope s(CAT_NTT); ntt_run(T, NS, NTT_INV, logn, w_ev[k].p, n, w_poly[k].p, st); }
-        Fq x, y; bool inf;
-        commit(w_poly[k].p, n, &comm[k], &x, &y, &inf);
-        tr.append_point(wl[k], x, y, inf);
+    {
+        // the four wire commitments do not depend on each other: one MSM batch
+        const fr_t* wp[4];
+        CommitmentC* wc[4];
+        Fq x[4], y[4]; bool inf[4];
+        for (int k = 0; k < 4; k++) {
+            { Scope s(CAT_NTT); ntt_run(T, NS, NTT_INV, logn, w_ev[k].p, n, w_poly[k].p, st); }
+            wp[k] = w_poly[k].p;
+            wc[k] = &comm[k];
+        }
+        commit_batch(wp, 4, n, wc, x, y, inf);
+        for (int k = 0; k < 4; k++) tr.append_point(wl[k], x[k], y[k], inf[k]);
     }
 
     // ---- 2. lookup polynomials (prover.rs:230-329)
@@ -586,12 +625,18 @@ void Prover::prove_resident(ProofC* out) {
     }
     static const char* tl[8] = {"t_1", "t_2", "t_3", "t_4", "t_5", "t_6", "t_7", "t_8"};
     bool t_zero[8];
-    for (int k = 0; k < 8; k++) {
-        Fq x, y; bool inf;
-        t_zero[k] = all_zero(PS, t_poly.p + (size_t)k * n, n, st);
-        if (t_zero[k]) commit(nullptr, 0, &comm[9 + k], &x, &y, &inf);
-        else commit(t_poly.p + (size_t)k * n, n, &comm[9 + k], &x, &y, &inf);
-        tr.append_point(tl[k], x, y, inf);
+    {
+        // t_1 .. t_8 are independent: one MSM batch over the non-zero ones (t_7 = t_8 = 0 for this circuit family)
+        const fr_t* tp[8];
+        CommitmentC* tc[8];
+        Fq x[8], y[8]; bool inf[8];
+        for (int k = 0; k < 8; k++) {
+            t_zero[k] = all_zero(PS, t_poly.p + (size_t)k * n, n, st);
+            tp[k] = t_zero[k] ? nullptr : t_poly.p + (size_t)k * n;
+            tc[k] = &comm[9 + k];
+        }
+        commit_batch(tp, 8, n, tc, x, y, inf);
+        for (int k = 0; k < 8; k++) tr.append_point(tl[k], x[k], y[k], inf[k]);
     }
 
     // ---- 5. linearisation (prover.rs:491-572, linearisation_poly.rs:164-372)
@@ -716,7 +761,9 @@ void Prover::prove_resident(ProofC* out) {
     for (int i = 0; i < NUM_E; i++) put_fr(eout + 4 * i, ev[i]);
 
     // ---- 6. openings (prover.rs:574-636; kzg10.cu:87-146)
-    auto open = [&](const std::vector<const fr_t*>& polys, const Fr& point, const Fr& chal, CommitmentC* dst) {
+    // both witness polynomials are built first (nothing is appended to the transcript between the two challenges),
+    // then committed as one MSM batch
+    auto open = [&](const std::vector<const fr_t*>& polys, const Fr& point, const Fr& chal, fr_t* wit_out) {
         std::vector<const fr_t*> lp;
         std::vector<fr_t> ls;
         Fr cj = Fr::one();
@@ -729,17 +776,22 @@ void Prover::prove_resident(ProofC* out) {
         }
         { Scope s(CAT_OTHER);
           lincomb(comb.p, lp.data(), ls.data(), (int)lp.size(), n, st);
-          divide_by_linear(PS, comb.p, n, D(point), wit.p, st); }
-        commit(wit.p, n, dst);
+          divide_by_linear(PS, comb.p, n, D(point), wit_out, st); }
     };
     Fr aw = tr.challenge_scalar("aggregate_witness");
     open({lin.p, coeffs[PK_SIGL].p, coeffs[PK_SIGR].p, coeffs[PK_SIGO].p, lookup_on ? f_poly.p : nullptr,
           lookup_on ? h2_poly.p : nullptr, lookup_on ? table_poly.p : nullptr, w_poly[0].p, w_poly[1].p, w_poly[2].p, w_poly[3].p},
-         z_ch, aw, &out->aw_opening);
+         z_ch, aw, wit.p);
     Fr saw = tr.challenge_scalar("aggregate_witness");
     open({z_poly.p, w_poly[0].p, w_poly[1].p, w_poly[3].p, lookup_on ? h1_poly.p : nullptr, z2_poly.p,
           lookup_on ? table_poly.p : nullptr},
-         zs, saw, &out->saw_opening);
+         zs, saw, wit2.p);
+    {
+        const fr_t* op[2] = {wit.p, wit2.p};
+        CommitmentC* oc[2] = {&out->aw_opening, &out->saw_opening};
+        Fq x[2], y[2]; bool inf[2];
+        commit_batch(op, 2, n, oc, x, y, inf);
+    }
 
     timer.end(total_id);
     timer.collect(last_ms);

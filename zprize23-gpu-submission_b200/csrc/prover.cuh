@@ -53,7 +53,7 @@ struct Prover {
     DevBuf<fr_t> z_poly, z8, z2_poly, z28;
     DevBuf<fr_t> t_ev, f_ev, h1_ev, h2_ev, table_poly, f_poly, h1_poly, h2_poly, tb8, f8, h18, h28;
     DevBuf<fr_t> quot, t_poly;
-    DevBuf<fr_t> num, den, lin, comb, wit;
+    DevBuf<fr_t> num, den, lin, comb, wit, wit2;
     double last_ms[5] = {0, 0, 0, 0, 0};
     // witness currently resident in w_ev / qlk_ev (set by upload_witness)
     size_t wit_n = 0;
@@ -62,8 +62,8 @@ struct Prover {
     bool wit_lookup_on = false;
     // per-proof MSM statistics (bucket-accumulation kernel, the dominant kernel of gen_proof)
     bool collect_msm_stats = false;
-    double msm_acc_ms = 0, msm_all_ms = 0, msm_mads = 0;
-    int msm_launches = 0;
+    double msm_acc_ms = 0, msm_all_ms = 0, msm_mads = 0, msm_exec_mads = 0;
+    int msm_launches = 0, msm_count = 0;  // MSM pipelines launched / commitments they produced
 
     // multi-GPU: every rank runs the whole protocol on identical inputs, but each KZG commitment's MSM is
     // sharded by point range; the per-rank partial sums (one XYZZ point, 192 B) are exchanged through the
@@ -89,6 +89,8 @@ struct Prover {
     void prove(const CircuitC& c, ProofC* out);
 
     host::G1 msm_over_srs(const fr_t* scalars_dev, size_t lo, size_t hi, size_t slice);
+    std::vector<host::G1> msm_over_srs_batch(const fr_t* const* scalars_dev, int k, size_t lo, size_t hi, size_t slice);
+    void commit_batch(const fr_t* const* coeffs_dev, int k, size_t ncoef, CommitmentC* const* outs, host::Fq* xs, host::Fq* ys, bool* infs);
     // commit to n coefficients (Montgomery) on the device; returns affine point (host)
     void commit(const fr_t* coeffs_dev, size_t ncoef, CommitmentC* out, host::Fq* ox = nullptr, host::Fq* oy = nullptr, bool* oinf = nullptr);
 };

@@ -167,6 +167,7 @@ def load_library(path=None):
         "zp_bench_download": (ci, [vp, ci, u64p, cs]),
         "zp_bench_ntt": (ci, [vp, ci, ci, ci, ci, ci, dp]),
         "zp_bench_msm": (ci, [vp, ci, cs, ci, dp, u64p]),
+        "zp_bench_msm_batch": (ci, [vp, ci, cs, ci, ci, dp, u64p]),
         "zp_bench_msm_breakdown": (ci, [vp, dp]),
         "zp_bench_int_pipe": (ci, [vp, ci, dp]),
         "zp_proof_serialize": (ci, [ctypes.POINTER(ProofC), ctypes.c_char_p, cs, ctypes.POINTER(cs)]),
@@ -187,7 +188,7 @@ EXPORTED_SYMBOLS = ["gen_proof", "zp_proof_serialize", "zp_proof_deserialize", "
                     "zp_prover_prove", "zp_prover_last_timing", "zp_prover_upload_witness", "zp_prover_prove_resident",
                     "zp_prover_collect_msm_stats", "zp_prover_msm_stats", "zp_prover_set_shard", "zp_prover_set_device_broadcast", "zp_ntt_host", "zp_ntt_sharded_host", "zp_bench_ntt_sharded", "zp_msm_host", "zp_msm_points_host",
                     "zp_poly_eval_host", "zp_poly_divide_host", "zp_prefix_product_host", "zp_combine_split_host", "zp_bench_alloc",
-                    "zp_bench_upload", "zp_bench_download", "zp_bench_ntt", "zp_bench_msm", "zp_bench_msm_breakdown",
+                    "zp_bench_upload", "zp_bench_download", "zp_bench_ntt", "zp_bench_msm", "zp_bench_msm_batch", "zp_bench_msm_breakdown",
                     "zp_bench_int_pipe"]
 
 
@@ -330,9 +331,10 @@ class ProverContext:
         self._ck(self.lib.zp_prover_collect_msm_stats(self.h, 1 if enable else 0))
 
     def msm_stats(self):
-        out = (ctypes.c_double * 4)()
+        out = (ctypes.c_double * 6)()
         self._ck(self.lib.zp_prover_msm_stats(self.h, out))
-        return {"accumulate_ms": out[0], "launches": int(out[1]), "algorithmic_mads": out[2], "all_kernels_ms": out[3]}
+        return {"accumulate_ms": out[0], "launches": int(out[1]), "algorithmic_mads": out[2], "all_kernels_ms": out[3],
+                "executed_mads": out[4], "commitments": int(out[5])}
 
     def set_shard(self, rank, world, allgather):
         """allgather(send_bytes: bytes) -> bytes of world * len(send_bytes) in rank order (e.g. torch.distributed)."""
@@ -448,13 +450,13 @@ class ProverContext:
         self._ck(self.lib.zp_bench_ntt(self.h, kind, log_n, slot_in, slot_out, iters, ctypes.byref(ms)))
         return ms.value
 
-    def bench_msm(self, slot, n, iters):
+    def bench_msm(self, slot, n, iters, nbatch=1):
         ms = ctypes.c_double()
         out = np.zeros(12, dtype=np.uint64)
-        self._ck(self.lib.zp_bench_msm(self.h, slot, n, iters, ctypes.byref(ms), as_u64p(out)))
-        bd = (ctypes.c_double * 5)()
+        self._ck(self.lib.zp_bench_msm_batch(self.h, slot, n, nbatch, iters, ctypes.byref(ms), as_u64p(out)))
+        bd = (ctypes.c_double * 6)()
         self._ck(self.lib.zp_bench_msm_breakdown(self.h, bd))
-        return ms.value, out, dict(zip(["digits", "scan", "scatter", "accumulate", "reduce"], list(bd)))
+        return ms.value, out, dict(zip(["digits", "scan", "scatter", "batch_affine", "accumulate", "reduce"], list(bd)))
 
     def bench_int_pipe(self, mode):
         g = ctypes.c_double()
