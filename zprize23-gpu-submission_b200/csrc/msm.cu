@@ -26,6 +26,7 @@ MsmConfig msm_config_for(size_t n, int c_override) {
     cfg.nbuckets = 1 << (c - 1);
     cfg.nsets = cfg.nwin;
     cfg.tab_stride = 0;
+    cfg.pt_stride = (uint32_t)sizeof(affine_t);
     return cfg;
 }
 
@@ -40,6 +41,7 @@ MsmConfig msm_config_precomp(size_t n, size_t tab_stride) {
     cfg.nbuckets = 1 << (c - 1);
     cfg.nsets = 1;
     cfg.tab_stride = tab_stride;
+    cfg.pt_stride = (uint32_t)sizeof(affine_pad_t);
     return cfg;
 }
 
@@ -73,8 +75,9 @@ void MsmWorkspace::reserve(size_t n, const MsmConfig& cfg, int nbatch) {
     }
     if (ba_rounds == 0) {
         const char* br = getenv("ZP_MSM_BA_ROUNDS");
-        // default 3 rounds: measured 25.3 -> 20.3 ms at 2^22 (profiles/r01b_msm_batch_affine.log); 0 disables
-        ba_rounds = br ? atoi(br) : 3;
+        // default 4 rounds: measured 25.4 -> 19.9 ms at 2^22, 17.5 ms per MSM in a batch of 4 (profiles/r01b_msm_*.log);
+        // 0 disables
+        ba_rounds = br ? atoi(br) : 4;
         ba_rounds_forced = br != nullptr;
         if (ba_rounds <= 0) ba_rounds = -1;  // disabled
         const char* bm = getenv("ZP_MSM_BA_MIN_LOG");
@@ -219,6 +222,10 @@ __global__ void __launch_bounds__(256) msm_scatter_kernel(const uint32_t* __rest
     sorted[pos] = (uint32_t)(tab_stride ? (size_t)w * tab_stride + i : i) | (dg & 0x80000000u);
 }
 
+// point number idx of an array whose elements are `stride` bytes apart (96: affine_t, 128: affine_pad_t)
+ZP_D const affine_t* point_at(const affine_t* base, uint32_t idx, uint32_t stride) {
+    return reinterpret_cast<const affine_t*>(reinterpret_cast<const unsigned char*>(base) + (size_t)idx * stride);
+}
 ZP_D affine_t load_affine(const affine_t* p) {
     affine_t r;
     r.x = load_fq(&p->x);
@@ -270,7 +277,7 @@ __global__ void __launch_bounds__(256) msm_segdesc_kernel(const uint32_t* __rest
 // from a global counter as soon as it finishes one, so all 32 lanes of a warp keep executing the same
 // point-addition body (no tail divergence from unequal bucket sizes).
 template <int MINBLOCKS>
-__global__ void __launch_bounds__(128, MINBLOCKS) msm_accumulate_kernel(const affine_t* __restrict__ points,
+__global__ void __launch_bounds__(128, MINBLOCKS) msm_accumulate_kernel(const affine_t* __restrict__ points, uint32_t pt_stride,
                                                                         const uint32_t* __restrict__ sorted,
                                                                         const uint2* __restrict__ desc,
                                                                         const uint32_t* __restrict__ nseg_ptr,
@@ -294,7 +301,7 @@ __global__ void __launch_bounds__(128, MINBLOCKS) msm_accumulate_kernel(const af
         // (software-pipelining the gather one iteration ahead was measured slower: 32.3 vs 30.1 ms — the loop is
         // multiplier-bound, the extra 24 live registers cost more than the hidden latency)
         uint32_t e = sorted ? sorted[k] : k;  // after batch-affine rounds the run IS the point array
-        affine_t p = load_affine(&points[e & 0x7fffffffu]);
+        affine_t p = load_affine(point_at(points, e & 0x7fffffffu, pt_stride));
         if (e >> 31) p.y = p.y.neg();
         acc.add_affine(p.x, p.y);
         k++;
@@ -383,25 +390,30 @@ __global__ void __launch_bounds__(128) msm_reduce_kernel(const xyzz_t* __restric
     if (threadIdx.x == 0) store_xyzz(&partial[blockIdx.x], sm[0]);
 }
 
-// one window row of the precomputed table: dst[i] = 2^c * src[i]  (c doublings in XYZZ, one inversion)
-__global__ void __launch_bounds__(128) msm_table_row_kernel(affine_t* __restrict__ dst, const affine_t* __restrict__ src, size_t n, int c) {
+// one window row of the precomputed table: dst[i] = 2^c * src[i]  (c doublings in XYZZ, one inversion); c == 0 copies
+__global__ void __launch_bounds__(128) msm_table_row_kernel(affine_pad_t* __restrict__ dst, const affine_t* __restrict__ src,
+                                                            uint32_t src_stride, size_t n, int c) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    affine_t p = load_affine(&src[i]);
-    xyzz_t a;
-    a.set_double_affine(p.x, p.y);
-    for (int k = 1; k < c; k++) a.dbl_inplace();
-    // the group has prime order, so 2^c * P is finite for finite P
-    fq_t inv = (a.ZZ * a.ZZZ).inverse();
-    fq_t zz_inv = inv * a.ZZZ, zzz_inv = inv * a.ZZ;
-    store_fq(&dst[i].x, a.X * zz_inv);
-    store_fq(&dst[i].y, a.Y * zzz_inv);
+    affine_t p = load_affine(point_at(src, (uint32_t)i, src_stride));
+    if (c > 0) {
+        xyzz_t a;
+        a.set_double_affine(p.x, p.y);
+        for (int k = 1; k < c; k++) a.dbl_inplace();
+        // the group has prime order, so 2^c * P is finite for finite P
+        fq_t inv = (a.ZZ * a.ZZZ).inverse();
+        fq_t zz_inv = inv * a.ZZZ, zzz_inv = inv * a.ZZ;
+        p.x = a.X * zz_inv;
+        p.y = a.Y * zzz_inv;
+    }
+    store_fq(&dst[i].x, p.x);
+    store_fq(&dst[i].y, p.y);
 }
-void msm_build_table(affine_t* dst, const affine_t* src, size_t n, int c, int nwin, cudaStream_t st) {
-    ZP_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(affine_t), cudaMemcpyDeviceToDevice, st));
+void msm_build_table(affine_pad_t* dst, const affine_t* src, size_t n, int c, int nwin, cudaStream_t st) {
+    ZP_LAUNCH(msm_table_row_kernel, dim3((unsigned)((n + 127) / 128)), dim3(128), 0, st, dst, src, (uint32_t)sizeof(affine_t), n, 0);
     for (int w = 1; w < nwin; w++)
         ZP_LAUNCH(msm_table_row_kernel, dim3((unsigned)((n + 127) / 128)), dim3(128), 0, st, dst + (size_t)w * n,
-                  dst + (size_t)(w - 1) * n, n, c);
+                  reinterpret_cast<const affine_t*>(dst + (size_t)(w - 1) * n), (uint32_t)sizeof(affine_pad_t), n, c);
 }
 
 }  // namespace zp
@@ -462,11 +474,12 @@ static void msm_launch_impl(MsmWorkspace& ws, const MsmConfig& cfg, const affine
     // ---- batch-affine pre-reduction rounds
     const uint32_t *run_begin = ws.start.p, *run_end = ws.cursor.p, *entries = ws.sorted.p;
     const affine_t* pts = points;
+    uint32_t pstride = cfg.pt_stride;  // the materialised partial sums of the batch-affine rounds are packed affine_t
     size_t est = wn;  // upper bound on the bucket entries still to be added
     int rounds = (allow_ba && wn >= ws.ba_min_entries) ? ws.ba_rounds : 0;
-    // leave >= 8 entries per bucket on average for the XYZZ pass (each round has a fixed cost of ~0.7 ms)
+    // leave >= 4 entries per bucket on average for the XYZZ pass (each round has a fixed cost of ~0.5 ms)
     if (!ws.ba_rounds_forced)
-        while (rounds > 0 && ((wn / wb) >> rounds) < 8) rounds--;
+        while (rounds > 0 && ((wn / wb) >> rounds) < 4) rounds--;
     ws.ba_used = rounds > 0;
     if (rounds > 0) {
         size_t cap0 = wn / 2 + wb;
@@ -491,15 +504,16 @@ static void msm_launch_impl(MsmWorkspace& ws, const MsmConfig& cfg, const affine
             msm_scan(ws.ba_cnt.p, rs, wb, ws.tile_sum.p, st);
             ZP_LAUNCH(ba_slots_kernel, dim3((unsigned)((wb * 32 + 255) / 256)), dim3(256), 0, st, run_begin, run_end, rs, wb,
                       ws.ba_src.p);
-            ZP_LAUNCH(ba_up0_kernel, dim3(nblk), dim3(BA_T), 0, st, ws.ba_src.p, rs + wb, cap, entries, pts, ws.ba_pre.p,
+            ZP_LAUNCH(ba_up0_kernel, dim3(nblk), dim3(BA_T), 0, st, ws.ba_src.p, rs + wb, cap, entries, pts, pstride, ws.ba_pre.p,
                       ws.ba_den.p, ws.ba_flag.p);
             fq_batch_inverse(ws.ba_den.p, m, ws.ba_den.p + m, st);
-            ZP_LAUNCH(ba_down0_kernel, dim3(nblk), dim3(BA_T), 0, st, ws.ba_src.p, rs + wb, cap, entries, pts, ws.ba_pre.p,
+            ZP_LAUNCH(ba_down0_kernel, dim3(nblk), dim3(BA_T), 0, st, ws.ba_src.p, rs + wb, cap, entries, pts, pstride, ws.ba_pre.p,
                       ws.ba_den.p, out);
             run_begin = rs;
             run_end = rs + 1;
             entries = nullptr;
             pts = out;
+            pstride = (uint32_t)sizeof(affine_t);
             est = cap;
         }
     }
@@ -531,13 +545,13 @@ static void msm_launch_impl(MsmWorkspace& ws, const MsmConfig& cfg, const affine
         unsigned grid = (unsigned)(ws.sm_count * blocks_per_sm);
         if (variant == 4) {
             auto k = msm_accumulate_kernel<4>;
-            ZP_LAUNCH(k, dim3(grid), dim3(128), 0, st, pts, entries, ws.desc.p, ws.seg_start.p + wb, ws.counter.p, ws.segs.p);
+            ZP_LAUNCH(k, dim3(grid), dim3(128), 0, st, pts, pstride, entries, ws.desc.p, ws.seg_start.p + wb, ws.counter.p, ws.segs.p);
         } else if (variant == 5) {
             auto k = msm_accumulate_kernel<5>;
-            ZP_LAUNCH(k, dim3(grid), dim3(128), 0, st, pts, entries, ws.desc.p, ws.seg_start.p + wb, ws.counter.p, ws.segs.p);
+            ZP_LAUNCH(k, dim3(grid), dim3(128), 0, st, pts, pstride, entries, ws.desc.p, ws.seg_start.p + wb, ws.counter.p, ws.segs.p);
         } else {
             auto k = msm_accumulate_kernel<3>;
-            ZP_LAUNCH(k, dim3(grid), dim3(128), 0, st, pts, entries, ws.desc.p, ws.seg_start.p + wb, ws.counter.p, ws.segs.p);
+            ZP_LAUNCH(k, dim3(grid), dim3(128), 0, st, pts, pstride, entries, ws.desc.p, ws.seg_start.p + wb, ws.counter.p, ws.segs.p);
         }
     }
     ZP_LAUNCH(msm_fold_small_kernel, dim3((unsigned)((wb + 127) / 128)), dim3(128), 0, st, ws.segs.p, ws.seg_start.p, wb);

@@ -14,6 +14,14 @@ struct MsmConfig {
     int nbuckets;       // buckets per bucket set = 2^(c-1)
     int nsets;          // bucket sets: nwin normally, 1 with precomputed window tables
     size_t tab_stride;  // 0, or the row stride of a precomputed table [w][i] = 2^(c w) * P_i
+    uint32_t pt_stride; // bytes between consecutive points: 96 (FFI affine_t) or 128 (padded table entries)
+};
+// Entry of a precomputed window table: one 128-byte line per point.  DRAM fills L2 in 128-byte lines on B200 (ncu:
+// 160 B fetched per random 48-byte x read, 192 B per 96-byte point with the packed 96-byte layout), so the random
+// gathers of the bucket accumulation cost exactly one line per point instead of 1.5 on average.
+struct alignas(128) affine_pad_t {
+    fq_t x, y;
+    uint32_t pad[8];
 };
 MsmConfig msm_config_for(size_t n, int c_override = 0);
 // start[0..m] = exclusive scan of cnt[0..m) (cnt is overwritten with the same prefix); tile_sum: m/2048 + 2 words of scratch
@@ -22,7 +30,7 @@ void u32_exclusive_scan(uint32_t* cnt, uint32_t* start, size_t m, uint32_t* tile
 // bucket set, so c can grow (fewer windows => fewer bucket additions) without multiplying the bucket count.
 MsmConfig msm_config_precomp(size_t n, size_t tab_stride);
 // dst[w * n + i] = 2^(c w) * src[i], w < nwin (dst may be larger than 4 GiB; built once per SRS)
-void msm_build_table(affine_t* dst, const affine_t* src, size_t n, int c, int nwin, cudaStream_t st);
+void msm_build_table(affine_pad_t* dst, const affine_t* src, size_t n, int c, int nwin, cudaStream_t st);
 
 // Several scalar vectors over the same points go through ONE pipeline (one bucket-set group per member): the
 // latency-bound stages (scans, inversion-tree tops, bucket reduction) are paid once per batch instead of once per MSM.

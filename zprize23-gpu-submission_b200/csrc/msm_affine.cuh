@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(256) ba_slots_kernel(const uint32_t* __restric
 
 // A CTA of BA_T threads covers BA_K * BA_T consecutive slots; thread tl owns slots base + k * BA_T + tl (k < BA_K), so
 // every per-slot array is read and written coalesced.  Those BA_K slots form one leaf group of the inversion tree.
-static const int BA_K = 8;
+static const int BA_K = 16;
 static const int BA_T = 256;
 
 // Leaf level of the batch inversion fused with the denominators den = x2 - x1 (1 for a leftover / unused / degenerate
@@ -44,8 +44,9 @@ static const int BA_T = 256;
 // The denominators themselves are not stored: the downward kernel reloads both points anyway.
 __global__ void __launch_bounds__(BA_T) ba_up0_kernel(const uint32_t* __restrict__ src0, const uint32_t* __restrict__ total_ptr,
                                                       size_t cap, const uint32_t* __restrict__ entries,
-                                                      const affine_t* __restrict__ pts, fq_t* __restrict__ pre,
-                                                      fq_t* __restrict__ up, uint32_t* __restrict__ flag) {
+                                                      const affine_t* __restrict__ pts, uint32_t pstride,
+                                                      fq_t* __restrict__ pre, fq_t* __restrict__ up,
+                                                      uint32_t* __restrict__ flag) {
     const size_t base = (size_t)blockIdx.x * (BA_K * BA_T) + threadIdx.x;
     const size_t total = *total_ptr;
     fq_t acc = fq_t::one();
@@ -60,7 +61,7 @@ __global__ void __launch_bounds__(BA_T) ba_up0_kernel(const uint32_t* __restrict
             if (s & 1u) {
                 const uint32_t i0 = s >> 1;
                 const uint32_t e0 = entries ? entries[i0] & 0x7fffffffu : i0, e1 = entries ? entries[i0 + 1] & 0x7fffffffu : i0 + 1;
-                d = load_fq(&pts[e1].x) - load_fq(&pts[e0].x);
+                d = load_fq(&point_at(pts, e1, pstride)->x) - load_fq(&point_at(pts, e0, pstride)->x);
                 pair = true;
                 if (d.is_zero()) {
                     *flag = 1;
@@ -80,8 +81,8 @@ __global__ void __launch_bounds__(BA_T) ba_up0_kernel(const uint32_t* __restrict
 // (2 products per slot with the stored prefix products) and emit out[j] = P(i0) + P(i0 + 1), or the leftover point.
 __global__ void __launch_bounds__(BA_T, 2) ba_down0_kernel(const uint32_t* __restrict__ src0, const uint32_t* __restrict__ total_ptr,
                                                         size_t cap, const uint32_t* __restrict__ entries,
-                                                        const affine_t* __restrict__ pts, const fq_t* __restrict__ pre,
-                                                        const fq_t* __restrict__ up_inv,
+                                                        const affine_t* __restrict__ pts, uint32_t pstride,
+                                                        const fq_t* __restrict__ pre, const fq_t* __restrict__ up_inv,
                                                         affine_t* __restrict__ out) {
     const size_t base = (size_t)blockIdx.x * (BA_K * BA_T) + threadIdx.x;
     const size_t total = *total_ptr;
@@ -94,11 +95,13 @@ __global__ void __launch_bounds__(BA_T, 2) ba_down0_kernel(const uint32_t* __res
         const uint32_t s = src0[j];
         const uint32_t i0 = s >> 1;
         const uint32_t e0 = entries ? entries[i0] : i0;
-        fq_t x1 = load_fq(&pts[e0 & 0x7fffffffu].x), y1 = load_fq(&pts[e0 & 0x7fffffffu].y);
+        const affine_t* p0 = point_at(pts, e0 & 0x7fffffffu, pstride);
+        fq_t x1 = load_fq(&p0->x), y1 = load_fq(&p0->y);
         if (entries && (e0 >> 31)) y1 = y1.neg();
         if (s & 1u) {
             const uint32_t e1 = entries ? entries[i0 + 1] : i0 + 1;
-            fq_t x2 = load_fq(&pts[e1 & 0x7fffffffu].x), y2 = load_fq(&pts[e1 & 0x7fffffffu].y);
+            const affine_t* p1 = point_at(pts, e1 & 0x7fffffffu, pstride);
+            fq_t x2 = load_fq(&p1->x), y2 = load_fq(&p1->y);
             if (entries && (e1 >> 31)) y2 = y2.neg();
             fq_t d = x2 - x1;
             if (!d.is_zero()) {  // a degenerate pair was given den = 1 (the whole MSM is redone anyway)

@@ -67,6 +67,15 @@ Prover::Prover(int logn_) : logn(logn_), n((size_t)1 << logn_), n8((size_t)8 << 
     const char* pm = getenv("ZP_MSM_PRECOMP_MIN_LOG");
     if (pm) precomp_min = (size_t)1 << atoi(pm);
     if (logn < 6 || logn + 3 > NTT_LMAX) throw std::runtime_error("zp_prover_create: log_n must be in [6, 23]");
+#ifndef ZP_EMU
+    // experiment knob: DRAM -> L2 fill granularity hint for the random 96-byte point gathers of the MSM (32 | 64 | 128)
+    if (const char* g = getenv("ZP_L2_FETCH")) {
+        ZP_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g)));
+        size_t got = 0;
+        cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
+        fprintf(stderr, "[zprize_b200] L2 fetch granularity set to %zu\n", got);
+    }
+#endif
     ZP_CUDA(cudaStreamCreate(&st));
     T.init(st);
     PS.init();
@@ -311,7 +320,7 @@ std::vector<host::G1> Prover::msm_over_srs_batch(const fr_t* const* scalars_dev,
             tab_n = slice;
         }
         cfg = tab_cfg;
-        base = srs_tab.p;
+        base = reinterpret_cast<const affine_t*>(srs_tab.p);
     }
     msm_launch_batch(MW, cfg, base, scalars_dev, k, hi - lo, st);
     std::vector<host::G1> r = msm_collect_batch(MW, cfg, st);

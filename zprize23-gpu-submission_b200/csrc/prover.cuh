@@ -34,7 +34,7 @@ struct Prover {
     // ---- resident inputs (uploaded / built once, reused by every proof)
     DevBuf<affine_t> srs;
     // precomputed window table of this rank's SRS slice [tab_lo, tab_lo + tab_n): T[w][i] = 2^(c w) * srs[tab_lo + i]
-    DevBuf<affine_t> srs_tab;
+    DevBuf<affine_pad_t> srs_tab;
     size_t tab_lo = 0, tab_n = 0;
     MsmConfig tab_cfg;
     bool use_precomp = true;
