@@ -223,8 +223,9 @@ int zp_bench_msm_batch(zp_prover* p, int slot, size_t n, int nbatch, int iters, 
 /* per-stage device time of the last zp_bench_msm iteration: digits, scan, scatter, batch-affine rounds,
  * accumulate (+ folds), reduce */
 int zp_bench_msm_breakdown(zp_prover* p, double* ms6);
-/* integer-pipe microbenchmark: mode 0 = IMAD (mad.lo), 1 = IMAD.WIDE (mad.wide), 2 = Fq Montgomery products,
- * 3 = Fq Montgomery squarings; returns giga-operations per second (instructions for 0/1, field operations for 2/3) */
+/* pipe microbenchmarks: mode 0 = IMAD (mad.lo), 1 = IMAD.WIDE (mad.wide), 2 = Fq Montgomery products,
+ * 3 = Fq Montgomery squarings, 4 = FP64 FMA, 5 = FP64 FMA interleaved 1:1 with IMAD (FP64 operations counted),
+ * 6 = 3-input integer add (ALU pipe); returns giga-operations per second (instructions, or field operations for 2/3) */
 int zp_bench_int_pipe(zp_prover* p, int mode, double* gops);
 
 #ifdef __cplusplus

@@ -23,6 +23,17 @@ def test_ntt_family(ctx, oracle, logn):
         assert np.array_equal(ctx.ntt(kind, x), oracle.ntt(kind, x)), (logn, kind)
 
 
+@pytest.mark.parametrize("logn", [10, 12])
+def test_ntt_direct_twiddle_tables(pkg, emu_lib, oracle, monkeypatch, logn):
+    """Same transforms when the inter-pass twiddles and the coset-iNTT output factors come from the direct tables."""
+    monkeypatch.setenv("ZP_NTT_TW_MIN_LOG", "0")
+    c = pkg.ProverContext(8, emu_lib)
+    x = oracle.random_fr(1, 1 << logn)
+    for kind in range(4):
+        assert np.array_equal(c.ntt(kind, x), oracle.ntt(kind, x)), (logn, kind)
+    c.close()
+
+
 def test_scans(ctx, oracle):
     x = oracle.random_fr(3, 3000)
     z = oracle.random_fr(4, 1)[0]

@@ -580,7 +580,7 @@ __global__ void int_pipe_kernel(int mode, int iters, uint32_t* sink) {
             y = y * x;
         }
         sink[tid] = x.l[0] ^ y.l[3];
-    } else {
+    } else if (mode == 3) {
         fq_t x = fq_t::one(), y = fq_t::rr();
         x.l[0] ^= tid;
         y.l[1] ^= tid;
@@ -589,6 +589,38 @@ __global__ void int_pipe_kernel(int mode, int iters, uint32_t* sink) {
             y = y.sqr();
         }
         sink[tid] = x.l[0] ^ y.l[3];
+    } else if (mode == 4 || mode == 5) {
+#ifndef ZP_EMU
+        // FP64 fused multiply-add pipe (mode 4), and the same interleaved 1:1 with integer multiply-adds (mode 5):
+        // measures whether a double-precision-limb multiplier could run beside / instead of the IMAD one (round-2 study)
+        double d0 = tid, d1 = tid + 1, d2 = tid + 2, d3 = tid + 3, d4 = tid + 4, d5 = tid + 5, d6 = tid + 6, d7 = tid + 7;
+        const double m = 1.0 + 1e-9 * tid;
+        uint32_t a0 = tid, a1 = tid + 1, a2 = tid + 2, a3 = tid + 3, a4 = tid + 4, a5 = tid + 5, a6 = tid + 6, a7 = tid + 7;
+        const uint32_t mi = tid | 1u;
+        for (int i = 0; i < iters; i++) {
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                d0 = __fma_rz(d0, m, d1); d1 = __fma_rz(d1, m, d2); d2 = __fma_rz(d2, m, d3); d3 = __fma_rz(d3, m, d4);
+                d4 = __fma_rz(d4, m, d5); d5 = __fma_rz(d5, m, d6); d6 = __fma_rz(d6, m, d7); d7 = __fma_rz(d7, m, d0);
+                if (mode == 5) {
+                    a0 = a0 * mi + a1; a1 = a1 * mi + a2; a2 = a2 * mi + a3; a3 = a3 * mi + a4;
+                    a4 = a4 * mi + a5; a5 = a5 * mi + a6; a6 = a6 * mi + a7; a7 = a7 * mi + a0;
+                }
+            }
+        }
+        sink[tid] = (uint32_t)__double_as_longlong(d0 + d1 + d2 + d3 + d4 + d5 + d6 + d7) ^ a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+#endif
+    } else {
+        // ALU pipe: 3-input integer adds (what the carry handling of an FP64-limb multiplier would issue)
+        uint32_t a0 = tid, a1 = tid + 1, a2 = tid + 2, a3 = tid + 3, a4 = tid + 4, a5 = tid + 5, a6 = tid + 6, a7 = tid + 7;
+        for (int i = 0; i < iters; i++) {
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                a0 = a0 + a1 + a2; a1 = a1 + a2 + a3; a2 = a2 + a3 + a4; a3 = a3 + a4 + a5;
+                a4 = a4 + a5 + a6; a5 = a5 + a6 + a7; a6 = a6 + a7 + a0; a7 = a7 + a0 + a1;
+            }
+        }
+        sink[tid] = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
     }
 }
 
@@ -597,7 +629,8 @@ extern "C" int zp_bench_int_pipe(zp_prover* p, int mode, double* gops) {
         Prover* pr = P(p);
         const int blocks = 148 * 8, threads = 256;
         DevBuf<uint32_t> sink((size_t)blocks * threads);
-        int iters = mode >= 2 ? 200 : 2000;
+        const bool field_op = mode == 2 || mode == 3;
+        int iters = field_op ? 200 : 2000;
         cudaEvent_t e0, e1;
         ZP_CUDA(cudaEventCreate(&e0));
         ZP_CUDA(cudaEventCreate(&e1));
@@ -608,7 +641,8 @@ extern "C" int zp_bench_int_pipe(zp_prover* p, int mode, double* gops) {
         ZP_CUDA(cudaEventSynchronize(e1));
         float t = 0;
         ZP_CUDA(cudaEventElapsedTime(&t, e0, e1));
-        double ops = (double)blocks * threads * iters * (mode >= 2 ? 2.0 : 64.0);
+        // mode 5 counts the FP64 operations only (an equal number of integer multiply-adds runs beside them)
+        double ops = (double)blocks * threads * iters * (field_op ? 2.0 : 64.0);
         *gops = ops / (t * 1e-3) / 1e9;
         cudaEventDestroy(e0);
         cudaEventDestroy(e1);

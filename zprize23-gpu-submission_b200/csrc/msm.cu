@@ -6,7 +6,7 @@
 //   3. scatter   : counting-sort the point indices into (window,bucket) runs (atomic cursor per bucket)
 //   4. accumulate: one thread per work segment (<= 2x mean bucket load) of a bucket, XYZZ mixed additions
 //                  (the IMAD-bound hot loop); long buckets are split so no digit distribution serialises
-//   5. reduce    : per window and bucket group, running-sum reduction  sum_b (b+1) * B_b  + tree in smem
+//   5. reduce    : row / column sums of the bucket matrix, then weight * sum and a tree (msm_rowcol_kernel, msm_weighted_kernel)
 //   host         : fold 8 partials per window, Horner over windows (256 doublings), to affine
 // Order inside a bucket is not deterministic (atomics) but the group sum is exact, so the affine
 // result is bit-identical run to run.
@@ -46,14 +46,10 @@ MsmConfig msm_config_precomp(size_t n, size_t tab_stride) {
 }
 
 static const int SCAN_TILE_FWD = 2048;
-// bucket groups per set for the reduce kernel: at least 128 CTAs in total, at least one bucket per thread
-static int msm_reduce_groups(const MsmConfig& cfg) {
-    int groups = MSM_REDUCE_GROUPS;
-    while (cfg.nsets * groups < 128) groups <<= 1;  // >= 128 CTAs (512 was measured slower: the per-thread scalar
-                                                    // multiplication by the bucket offset then dominates)
-    while (groups > 1 && cfg.nbuckets / groups < 1) groups >>= 1;
-    return groups;
-}
+// bucket matrix of the reduction (see msm_rowcol_kernel): 2^lw2 columns
+static int msm_reduce_lw2(const MsmConfig& cfg) { return cfg.c / 2; }  // nbuckets = 2^(c-1): W2 >= W1
+static int msm_reduce_entries(const MsmConfig& cfg) { return (cfg.nbuckets >> msm_reduce_lw2(cfg)) + (1 << msm_reduce_lw2(cfg)); }
+static int msm_reduce_groups(const MsmConfig& cfg) { return (msm_reduce_entries(cfg) + 127) / 128; }
 
 void MsmWorkspace::reserve(size_t n, const MsmConfig& cfg, int nbatch) {
     size_t wn = (size_t)nbatch * cfg.nwin * n, wb = (size_t)nbatch * cfg.nsets * cfg.nbuckets;
@@ -88,6 +84,7 @@ void MsmWorkspace::reserve(size_t n, const MsmConfig& cfg, int nbatch) {
     size_t np = nsets * msm_reduce_groups(cfg);
     if (partial.n < np) partial.alloc(np);
     if (final_sums.n < nsets) final_sums.alloc(nsets);
+    if (rowcol.n < nsets * msm_reduce_entries(cfg)) rowcol.alloc(nsets * msm_reduce_entries(cfg));
     if (np < nsets) np = nsets;
     if (partial_host.size() < np) partial_host.resize(np);
 }
@@ -352,34 +349,60 @@ ZP_D xyzz_t load_bucket(const xyzz_t* __restrict__ segs, const uint32_t* __restr
     return load_xyzz(&segs[s0]);
 }
 
-// One CTA per (window, bucket group).  partial[w * G + g] = sum_{b in group} (b + 1) * bucket[w][b]
-__global__ void __launch_bounds__(128) msm_reduce_kernel(const xyzz_t* __restrict__ segs, const uint32_t* __restrict__ seg_start,
-                                                         int nbuckets, int groups, xyzz_t* __restrict__ partial) {
-    ZP_DYN_SMEM(xyzz_t, sm);
-    const int w = blockIdx.x / groups, g = blockIdx.x % groups;
-    const int bg = nbuckets / groups;          // buckets per group
-    const int T = blockDim.x;
-    const int L = bg / T;                      // buckets per thread (host guarantees divisibility, L >= 1)
-    const int j0 = g * bg + threadIdx.x * L;   // first bucket of this thread (weight j0 + 1)
-    const size_t B0 = (size_t)w * nbuckets;
-    xyzz_t run = xyzz_t::infinity(), sum = xyzz_t::infinity();
-    for (int j = j0 + L - 1; j >= j0; j--) {
-        xyzz_t b = load_bucket(segs, seg_start, B0 + j);
-        run.add(b);
-        sum.add(run);
+// Bucket reduction  sum_j (j + 1) * B_j  of one bucket set in two short steps instead of one long running sum.
+// With j = j1 * W2 + j2 (W2 = 2^lw2 columns, W1 rows):
+//     sum_j (j + 1) B_j  =  sum_{j1} (j1 * W2) * R_{j1}  +  sum_{j2} (j2 + 1) * C_{j2}
+// where R_{j1} / C_{j2} are the plain row / column sums of the bucket matrix.  Step 1 (msm_rowcol_kernel) computes the
+// W1 + W2 plain sums, one CTA each (throughput-bound, 2 additions per bucket in total); step 2 (msm_weighted_kernel)
+// multiplies each of them by its <= c-bit weight and tree-adds.  The dependent chain is ~30 additions long instead of
+// the ~100 of a 128-thread running sum over 2^19 buckets, which was latency-bound at 1.9 ms per MSM.
+// rc[set][0 .. W1) = R_{j1} (entry 0 has weight 0 and is never read), rc[set][W1 .. W1 + W2) = C_{j2}.
+__global__ void __launch_bounds__(128) msm_rowcol_kernel(const xyzz_t* __restrict__ segs, const uint32_t* __restrict__ seg_start,
+                                                         int nbuckets, int lw2, xyzz_t* __restrict__ rc) {
+    __shared__ xyzz_t sm[128];
+    const int W2 = 1 << lw2, W1 = nbuckets >> lw2, E = W1 + W2;
+    const int set = blockIdx.x / E, o = blockIdx.x % E;
+    const size_t B0 = (size_t)set * nbuckets;
+    xyzz_t acc = xyzz_t::infinity();
+    if (o < W1) {
+        if (o == 0) return;  // weight 0
+        for (int m = threadIdx.x; m < W2; m += blockDim.x) acc.add(load_bucket(segs, seg_start, B0 + (size_t)o * W2 + m));
+    } else {
+        const int j2 = o - W1;
+        for (int m = threadIdx.x; m < W1; m += blockDim.x) acc.add(load_bucket(segs, seg_start, B0 + (size_t)m * W2 + j2));
     }
-    // sum = sum_j (j - j0 + 1) B_j ;  add j0 * run
-    if (j0) {
-        xyzz_t acc = xyzz_t::infinity();
-        for (int bit = 31 - __clz((uint32_t)j0); bit >= 0; bit--) {
-            acc.dbl_inplace();
-            if ((j0 >> bit) & 1) acc.add(run);
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for (int d = blockDim.x >> 1; d >= 1; d >>= 1) {
+        if ((int)threadIdx.x < d) {
+            xyzz_t a = sm[threadIdx.x];
+            a.add(sm[threadIdx.x + d]);
+            sm[threadIdx.x] = a;
         }
-        sum.add(acc);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) store_xyzz(&rc[blockIdx.x], sm[0]);
+}
+
+// partial[set * G + g] = sum over the g-th 128 entries of rc[set] of weight * entry  (G = ceil((W1 + W2) / 128))
+__global__ void __launch_bounds__(128) msm_weighted_kernel(const xyzz_t* __restrict__ rc, int nbuckets, int lw2, int groups,
+                                                           xyzz_t* __restrict__ partial) {
+    __shared__ xyzz_t sm[128];
+    const int W2 = 1 << lw2, W1 = nbuckets >> lw2, E = W1 + W2;
+    const int set = blockIdx.x / groups, g = blockIdx.x % groups;
+    const int o = g * 128 + threadIdx.x;
+    xyzz_t sum = xyzz_t::infinity();
+    if (o < E && o != 0) {
+        const uint32_t wgt = o < W1 ? (uint32_t)o << lw2 : (uint32_t)(o - W1 + 1);
+        const xyzz_t v = load_xyzz(&rc[(size_t)set * E + o]);
+        for (int bit = 31 - __clz(wgt); bit >= 0; bit--) {
+            sum.dbl_inplace();
+            if ((wgt >> bit) & 1) sum.add(v);
+        }
     }
     sm[threadIdx.x] = sum;
     __syncthreads();
-    for (int d = T >> 1; d >= 1; d >>= 1) {
+    for (int d = 64; d >= 1; d >>= 1) {
         if ((int)threadIdx.x < d) {
             xyzz_t a = sm[threadIdx.x];
             a.add(sm[threadIdx.x + d]);
@@ -557,11 +580,11 @@ static void msm_launch_impl(MsmWorkspace& ws, const MsmConfig& cfg, const affine
     ZP_LAUNCH(msm_fold_small_kernel, dim3((unsigned)((wb + 127) / 128)), dim3(128), 0, st, ws.segs.p, ws.seg_start.p, wb);
     ZP_LAUNCH(msm_fold_kernel, dim3((unsigned)((wb + 3) / 4)), dim3(128), 0, st, ws.segs.p, ws.seg_start.p, wb);
     mark(5);
-    int groups = msm_reduce_groups(cfg);
-    int bg = cfg.nbuckets / groups;
-    int T = bg < 128 ? bg : 128;
-    ZP_LAUNCH(msm_reduce_kernel, dim3(nsets * groups), dim3(T), (size_t)T * sizeof(xyzz_t), st, ws.segs.p, ws.seg_start.p,
-              cfg.nbuckets, groups, ws.partial.p);
+    const int groups = msm_reduce_groups(cfg), lw2 = msm_reduce_lw2(cfg);
+    ZP_LAUNCH(msm_rowcol_kernel, dim3((unsigned)(nsets * msm_reduce_entries(cfg))), dim3(128), 0, st, ws.segs.p, ws.seg_start.p,
+              cfg.nbuckets, lw2, ws.rowcol.p);
+    ZP_LAUNCH(msm_weighted_kernel, dim3((unsigned)(nsets * groups)), dim3(128), 0, st, ws.rowcol.p, cfg.nbuckets, lw2, groups,
+              ws.partial.p);
     ZP_LAUNCH(msm_final_kernel, dim3(nsets), dim3(128), 0, st, ws.partial.p, groups, ws.final_sums.p);
     mark(6);
     ZP_CUDA(cudaMemcpyAsync(ws.partial_host.data(), ws.final_sums.p, (size_t)nsets * sizeof(xyzz_t), cudaMemcpyDeviceToHost, st));

@@ -73,7 +73,8 @@ struct MsmWorkspace {
     int ba_rounds_used = 0;    // batch-affine rounds of the last launch
     size_t seg = 0;            // points per work segment (2x the mean bucket load, >= 32)
     size_t max_segs = 0;
-    DevBuf<xyzz_t> partial;    // [nwin * MSM_REDUCE_GROUPS]
+    DevBuf<xyzz_t> rowcol;     // [nsets][W1 + W2] row / column sums of the bucket matrix (bucket reduction, step 1)
+    DevBuf<xyzz_t> partial;    // [nsets][groups] weighted partial sums (bucket reduction, step 2)
     DevBuf<xyzz_t> final_sums; // [nsets] per-set sums (what returns to the host)
     std::vector<xyzz_t> partial_host;
     // optional per-stage timing (bench only): digits, scan, scatter, batch-affine rounds, accumulate (+ folds), reduce
@@ -82,7 +83,6 @@ struct MsmWorkspace {
     double last_ms[6] = {0, 0, 0, 0, 0, 0};
     void reserve(size_t n, const MsmConfig& cfg, int nbatch = 1);
 };
-static const int MSM_REDUCE_GROUPS = 8;
 
 // result = sum_i scalars[i] * points[i]; scalars are Montgomery Fr (as they live in polynomial buffers;
 // the canonical conversion the reference does as a separate `to_base` pass is fused into the digit kernel).

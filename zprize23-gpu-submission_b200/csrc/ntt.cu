@@ -57,6 +57,8 @@ void NttTables::init(cudaStream_t st) {
     ZP_LAUNCH(power_table_kernel, dim3((HI + 255) / 256), dim3(256), 0, st, g_hi.p, g, NTT_LO_BITS, HI);
     ZP_LAUNCH(power_table_kernel, dim3((LO + 255) / 256), dim3(256), 0, st, gi_lo.p, gi, 0, LO);
     ZP_LAUNCH(power_table_kernel, dim3((HI + 255) / 256), dim3(256), 0, st, gi_hi.p, gi, NTT_LO_BITS, HI);
+    if (const char* e = getenv("ZP_NTT_TW_MAX_LOG")) tw_max_log = atoi(e);
+    if (const char* e = getenv("ZP_NTT_TW_MIN_LOG")) tw_min_log = atoi(e);
     ready = true;
 }
 
@@ -70,6 +72,8 @@ struct NttPassParams {
     int coset;      // 0 none, 1 multiply input by g^n (first pass), 2 multiply output by g^-k (last pass)
     size_t n_in;    // elements >= n_in of the input are implicit zeros (first pass only)
     const fr_t *w_lo, *w_hi, *c_lo, *c_hi;
+    const fr_t* tw;      // direct inter-pass twiddle table [(n << lk) | ks] of this pass, or null (two-level lookup)
+    const fr_t* out_tw;  // direct output factors 2^-logn * 7^-pos of the coset iNTT, or null
     fr_t ninv;      // 2^-logn (used when inverse && last)
 };
 
@@ -122,8 +126,12 @@ __global__ void __launch_bounds__(1024) ntt_pass_kernel(const fr_t* __restrict__
             uint32_t ks = (uint32_t)q & ((1u << p.lk) - 1);
             uint32_t ex = ((uint32_t)n * ks) << (NTT_LMAX - (p.lk + p.lr));  // theta = omega_{T_{p+1}}
             if (ex) {
-                if (p.inverse) ex = ((1u << NTT_LMAX) - ex) & emask;
-                v = v * tw_lookup(p.w_lo, p.w_hi, ex);
+                if (p.tw) {
+                    v = v * load_fr(&p.tw[((size_t)n << p.lk) | ks]);
+                } else {
+                    if (p.inverse) ex = ((1u << NTT_LMAX) - ex) & emask;
+                    v = v * tw_lookup(p.w_lo, p.w_hi, ex);
+                }
             }
         }
         sm_store(sm, RC, e, v);
@@ -171,7 +179,9 @@ __global__ void __launch_bounds__(1024) ntt_pass_kernel(const fr_t* __restrict__
         int row = p.lr ? (int)(__brev((uint32_t)k) >> sh) : 0;
         fr_t v = sm_load(sm, RC, row * C + c);
         if (p.last) {
-            if (p.coset == 2) {
+            if (p.coset == 2 && p.out_tw) {
+                v = v * load_fr(&p.out_tw[pos]);
+            } else if (p.coset == 2) {
                 uint32_t lo = (uint32_t)pos & ((1u << NTT_LO_BITS) - 1), hi = (uint32_t)(pos >> NTT_LO_BITS);
                 fr_t f = p.ninv;
                 if (lo) f = f * load_fr(&p.c_lo[lo]);
@@ -183,6 +193,55 @@ __global__ void __launch_bounds__(1024) ntt_pass_kernel(const fr_t* __restrict__
         }
         store_fr(&out[pos], v);
     }
+}
+
+// tw[(n << lk) | ks] = omega_{2^(lk+lr)}^{+- n * ks}
+__global__ void ntt_pass_table_kernel(fr_t* __restrict__ tw, int lr, int lk, int inverse, const fr_t* __restrict__ w_lo,
+                                      const fr_t* __restrict__ w_hi) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >> (lr + lk)) return;
+    uint32_t n = (uint32_t)(idx >> lk), ks = (uint32_t)idx & ((1u << lk) - 1);
+    uint32_t ex = (n * ks) << (NTT_LMAX - (lk + lr));
+    if (inverse) ex = ((1u << NTT_LMAX) - ex) & ((1u << NTT_LMAX) - 1);
+    store_fr(&tw[idx], ex ? tw_lookup(w_lo, w_hi, ex) : fr_t::one());
+}
+// out[pos] = ninv * 7^-pos
+__global__ void ntt_coset_out_table_kernel(fr_t* __restrict__ out, size_t n, fr_t ninv, const fr_t* __restrict__ c_lo,
+                                           const fr_t* __restrict__ c_hi) {
+    size_t pos = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= n) return;
+    uint32_t lo = (uint32_t)pos & ((1u << NTT_LO_BITS) - 1), hi = (uint32_t)(pos >> NTT_LO_BITS);
+    fr_t f = ninv;
+    if (lo) f = f * load_fr(&c_lo[lo]);
+    if (hi) f = f * load_fr(&c_hi[hi]);
+    store_fr(&out[pos], f);
+}
+const fr_t* NttTables::pass_table(int logn, int inverse, int lr, int lk, cudaStream_t st) const {
+    if (lr + lk > tw_max_log) return nullptr;
+    // the table depends on (lr, lk, direction) only: omega_{2^(lk+lr)}
+    uint32_t key = (uint32_t)lr | ((uint32_t)lk << 8) | ((uint32_t)(inverse ? 1 : 0) << 16);
+    (void)logn;
+    auto it = direct.find(key);
+    if (it == direct.end()) {
+        DevBuf<fr_t> b((size_t)1 << (lr + lk));
+        size_t cnt = (size_t)1 << (lr + lk);
+        ZP_LAUNCH(ntt_pass_table_kernel, dim3((unsigned)((cnt + 255) / 256)), dim3(256), 0, st, b.p, lr, lk, inverse, w_lo.p, w_hi.p);
+        it = direct.emplace(key, std::move(b)).first;
+    }
+    return it->second.p;
+}
+const fr_t* NttTables::coset_out_table(int logn, cudaStream_t st) const {
+    if (logn > tw_max_log) return nullptr;
+    uint32_t key = 0x80000000u | (uint32_t)logn;
+    auto it = direct.find(key);
+    if (it == direct.end()) {
+        size_t cnt = (size_t)1 << logn;
+        DevBuf<fr_t> b(cnt);
+        ZP_LAUNCH(ntt_coset_out_table_kernel, dim3((unsigned)((cnt + 255) / 256)), dim3(256), 0, st, b.p, cnt, ninv[logn], gi_lo.p,
+                  gi_hi.p);
+        it = direct.emplace(key, std::move(b)).first;
+    }
+    return it->second.p;
 }
 
 void ntt_run(const NttTables& T, NttScratch& S, NttKind kind, int logn, const fr_t* in, size_t n_in, fr_t* out,
@@ -241,6 +300,8 @@ void ntt_run(const NttTables& T, NttScratch& S, NttKind kind, int logn, const fr
         pp.c_lo = (kind == NTT_COSET_FWD) ? T.g_lo.p : T.gi_lo.p;
         pp.c_hi = (kind == NTT_COSET_FWD) ? T.g_hi.p : T.gi_hi.p;
         pp.ninv = T.ninv[logn];
+        pp.tw = (p > 0 && logn >= T.tw_min_log) ? T.pass_table(logn, inverse ? 1 : 0, pp.lr, lk, st) : nullptr;
+        pp.out_tw = (last && kind == NTT_COSET_INV && logn >= T.tw_min_log) ? T.coset_out_table(logn, st) : nullptr;
         int RC = 1 << (pp.lr + pp.lc);
         size_t smem = (size_t)RC * 32;
         int threads = RC / 2 < max_threads ? (RC / 2 < 32 ? 32 : RC / 2) : max_threads;

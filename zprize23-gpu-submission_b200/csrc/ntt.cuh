@@ -5,6 +5,7 @@
 // `GeneralEvaluationDomain::{fft, ifft, coset_fft, coset_ifft}`.
 #pragma once
 #include "common.cuh"
+#include <map>
 
 namespace zp {
 
@@ -24,6 +25,15 @@ struct NttTables {
     fr_t omega_inv[NTT_LMAX + 1];
     bool ready = false;
     void init(cudaStream_t st);
+    // Direct per-pass tables (built on first use, resident afterwards): the inter-pass twiddle omega_N^{n * ks} of pass p as
+    // tw[(n << lk) | ks], and for the coset iNTT the output factor 2^-logn * 7^-pos as out[pos].  One load + ONE product per
+    // element instead of the two-level lookup's two (three for the coset output); costs 32 B of extra HBM read per element on
+    // a pass that is multiplier-bound.  Tables above 2^tw_max_log entries are not built (two-level lookup is used instead).
+    mutable std::map<uint32_t, DevBuf<fr_t>> direct;
+    int tw_max_log = 25;  // ZP_NTT_TW_MAX_LOG; 0 disables
+    int tw_min_log = 16;  // transforms below 2^tw_min_log keep the two-level lookup (ZP_NTT_TW_MIN_LOG)
+    const fr_t* pass_table(int logn, int inverse, int lr, int lk, cudaStream_t st) const;
+    const fr_t* coset_out_table(int logn, cudaStream_t st) const;
 };
 
 struct NttScratch {
