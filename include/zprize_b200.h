@@ -196,6 +196,10 @@ int zp_bench_ntt_sharded(zp_prover* p, int kind, int log_n, int rank, int world,
                          int slot_tmp_b, int iters, zp_dev_alltoall_fn alltoall, void* user, double* ms);
 /* MSM over the first n points of the resident SRS with n host scalars (Montgomery Fr). out: affine. */
 int zp_msm_host(zp_prover* p, const uint64_t* scalars, size_t n, uint64_t* out_affine);
+/* nbatch (<= 8) MSMs over the same first n SRS points in ONE pipeline: scalars = nbatch * n Montgomery Fr (member-major),
+ * out = nbatch affine points.  This is the path gen_proof uses for independent commitments (the four wire
+ * polynomials, t_1..t_8, the two opening witnesses; reference: one multi_scalar_mult call each, gen_proof.cuh). */
+int zp_msm_batch_host(zp_prover* p, const uint64_t* scalars, int nbatch, size_t n, uint64_t* out_affine);
 /* MSM with caller-supplied points (n * 12 u64, host). window_bits = 0 picks the default. */
 int zp_msm_points_host(zp_prover* p, const uint64_t* points, const uint64_t* scalars, size_t n, int window_bits,
                        uint64_t* out_affine);

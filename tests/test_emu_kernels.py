@@ -111,6 +111,24 @@ def test_msm_batch_affine_rounds(pkg, emu_lib, oracle, monkeypatch, rounds):
     ctx.close()
 
 
+def test_msm_batch_members(pkg, emu_lib, oracle, monkeypatch):
+    """Several scalar vectors in one MSM pipeline (with and without the precomputed table / batch-affine rounds)."""
+    n = 600
+    srs, _ = oracle.srs(7, 1024)
+    pts = srs[:n].copy()
+    sc = np.stack([oracle.random_fr(40 + j, n) for j in range(3)])
+    sc[1] = 0
+    for env in ({}, {"ZP_MSM_PRECOMP_MIN_LOG": "8", "ZP_MSM_BA_ROUNDS": "2", "ZP_MSM_BA_MIN_LOG": "4"}):
+        for key, val in env.items():
+            monkeypatch.setenv(key, val)
+        c = pkg.ProverContext(10, emu_lib)
+        c.load_srs(srs)
+        out = c.msm_batch(sc)
+        for j in range(3):
+            assert np.array_equal(out[j], oracle.msm(pts, sc[j].copy())), (env, j)
+        c.close()
+
+
 def test_gen_proof_with_batch_affine_and_tables(pkg, emu_lib, oracle, monkeypatch):
     monkeypatch.setenv("ZP_MSM_PRECOMP_MIN_LOG", "8")
     monkeypatch.setenv("ZP_MSM_BA_ROUNDS", "2")

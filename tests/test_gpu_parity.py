@@ -213,6 +213,28 @@ def test_batch_affine_msm_on_device(pkg, gpu_lib, oracle, monkeypatch):
     ctx.close()
 
 
+@pytest.mark.parametrize("logn,k", [(10, 3), (16, 5), (18, 8)])
+def test_msm_batch_matches_oracle(pkg, gpu_lib, oracle, logn, k):
+    """k scalar vectors over the same SRS points through ONE MSM pipeline (the path of the prover's independent
+    commitments): every member equals the oracle's single MSM; members include an all-zero vector and repeated scalars.
+    2^16 and 2^18 go through the precomputed window table and the batch-affine rounds."""
+    n = 1 << logn
+    ctx = pkg.ProverContext(logn, gpu_lib)
+    pts, tau = oracle.srs(7, n)
+    ctx.generate_srs(tau)
+    sc = np.stack([oracle.random_fr(30 + j, n) for j in range(k)])
+    sc[1] = 0
+    sc[2, : n // 2] = sc[2, 0]
+    out = ctx.msm_batch(sc)
+    for j in range(k):
+        if logn <= 16 or j < 3:
+            assert np.array_equal(out[j], oracle.msm(pts, sc[j].copy())), (logn, j)
+    # same members one by one through the single-MSM entry point
+    for j in (0, k - 1):
+        assert np.array_equal(out[j], ctx.msm(sc[j].copy()))
+    ctx.close()
+
+
 def test_combine_split_on_device(ctx16, oracle, pkg):
     def small(vals):
         a = np.zeros((len(vals), 4), dtype=np.uint64)

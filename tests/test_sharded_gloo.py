@@ -1,6 +1,7 @@
-"""world_size-2 test of the multi-GPU path on CPU: two processes (gloo) each run the product's prover under the
-emulation layer with MSMs sharded by point range and the partial sums exchanged by all-gather; both ranks must
-produce the oracle's proof bytes."""
+"""world_size-2 / -4 tests of the multi-GPU path on CPU: the processes (gloo) each run the product's prover under the
+emulation layer with MSMs sharded by point range (partial sums exchanged by all-gather) and the quotient round sharded by
+cosets of the extended domain (per-coset coefficient vectors broadcast, size-8 DFT across cosets); every rank must produce
+the oracle's proof bytes, with and without lookups."""
 import os
 import socket
 import sys
@@ -21,7 +22,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, emu_path, out_dir):
+def _worker(rank, world, port, emu_path, out_dir, n_lookup=0):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     sys.path.insert(0, ROOT)
     from conftest import load_package
@@ -32,7 +33,7 @@ def _worker(rank, world, port, emu_path, out_dir):
     pkg = load_package()
     lib = pkg.load_library(emu_path)
     orc = oracle_lib.load()
-    oc = oracle_lib.OracleCircuit(orc, 3, 42, 7, 0)
+    oc = oracle_lib.OracleCircuit(orc, 3, 42, 7, n_lookup)
     ctx = pkg.ProverContext(oc.log_n, lib)
     ctx.load_srs(oc.srs())
     ctx.preprocess(oc.selector_evals(), oc.tables())
@@ -60,13 +61,16 @@ def _worker(rank, world, port, emu_path, out_dir):
     dist.destroy_process_group()
 
 
-def test_sharded_msm_two_ranks(pkg, oracle, tmp_path):
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("world,n_lookup", [(2, 0), (4, 12)])
+def test_sharded_msm_two_ranks(pkg, oracle, tmp_path, world, n_lookup):
     import oracle_lib
     emu_path = pkg._build.build_emu()
     oracle_lib.load()
-    world = 2
-    mp.spawn(_worker, args=(world, _free_port(), emu_path, str(tmp_path)), nprocs=world, join=True)
-    oc = oracle_lib.OracleCircuit(oracle, 3, 42, 7, 0)
+    mp.spawn(_worker, args=(world, _free_port(), emu_path, str(tmp_path), n_lookup), nprocs=world, join=True)
+    oc = oracle_lib.OracleCircuit(oracle, 3, 42, 7, n_lookup)
     ref, _ = oc.prove()
     for r in range(world):
         assert np.array_equal(np.load(os.path.join(str(tmp_path), "proof_%d.npy" % r)), ref)

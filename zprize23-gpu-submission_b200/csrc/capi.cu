@@ -404,6 +404,19 @@ int zp_msm_host(zp_prover* p, const uint64_t* scalars, size_t n, uint64_t* out_a
         msm_to_affine_out(pr->msm_over_srs(s.p, 0, n, pr->srs.n), out_affine);
     });
 }
+int zp_msm_batch_host(zp_prover* p, const uint64_t* scalars, int nbatch, size_t n, uint64_t* out_affine) {
+    return guard([&] {
+        Prover* pr = P(p);
+        if (n > pr->srs.n) throw std::runtime_error("zp_msm_batch_host: more scalars than resident SRS points");
+        if (nbatch < 1 || nbatch > MSM_MAX_BATCH) throw std::runtime_error("zp_msm_batch_host: batch size must be in [1, 8]");
+        DevBuf<fr_t> s((size_t)nbatch * n);
+        ZP_CUDA(cudaMemcpyAsync(s.p, scalars, (size_t)nbatch * n * sizeof(fr_t), cudaMemcpyHostToDevice, pr->st));
+        const fr_t* sp[MSM_MAX_BATCH];
+        for (int k = 0; k < nbatch; k++) sp[k] = s.p + (size_t)k * n;
+        std::vector<host::G1> r = pr->msm_over_srs_batch(sp, nbatch, 0, n, pr->srs.n);
+        for (int k = 0; k < nbatch; k++) msm_to_affine_out(r[k], out_affine + 12 * k);
+    });
+}
 int zp_msm_points_host(zp_prover* p, const uint64_t* points, const uint64_t* scalars, size_t n, int window_bits,
                        uint64_t* out_affine) {
     return guard([&] {

@@ -324,6 +324,78 @@ void ntt_run(const NttTables& T, NttScratch& S, NttKind kind, int logn, const fr
 
 }  // namespace zp
 
+namespace zp {
+
+__global__ void __launch_bounds__(256) ntt_coset_shift_kernel(const fr_t* __restrict__ in, fr_t* __restrict__ out, size_t n,
+                                                              int logn_big, uint32_t j, int inverse,
+                                                              const fr_t* __restrict__ w_lo, const fr_t* __restrict__ w_hi) {
+    size_t m = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n) return;
+    fr_t v = load_fr(&in[m]);
+    uint32_t e = (uint32_t)(((uint64_t)j * m) & (((uint64_t)1 << logn_big) - 1));
+    uint32_t ex = e << (NTT_LMAX - logn_big);
+    if (ex) {
+        if (inverse) ex = ((1u << NTT_LMAX) - ex) & ((1u << NTT_LMAX) - 1);
+        v = v * tw_lookup(w_lo, w_hi, ex);
+    }
+    store_fr(&out[m], v);
+}
+void ntt_coset_shift(const NttTables& T, const fr_t* in, fr_t* out, size_t n, int logn_big, int j, bool inverse, cudaStream_t st) {
+    if (!n) return;
+    ZP_LAUNCH(ntt_coset_shift_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, in, out, n, logn_big, (uint32_t)j,
+              inverse ? 1 : 0, T.w_lo.p, T.w_hi.p);
+}
+
+struct Combine8Consts {
+    fr_t w[4];      // w_8^-e, e < 4
+    fr_t scale[8];  // g^(-N m') / 8
+};
+// size-8 inverse DFT across the cosets (radix-2 DIF, result index bit-reversed), one thread per coefficient index m
+__global__ void __launch_bounds__(128) ntt_combine8_kernel(const fr_t* __restrict__ PJ, fr_t* __restrict__ t_out, size_t n,
+                                                           Combine8Consts c) {
+    size_t m = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n) return;
+    fr_t x[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) x[j] = load_fr(&PJ[(size_t)j * n + m]);
+#pragma unroll
+    for (int s = 0; s < 3; s++) {
+        const int half = 4 >> s;
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int jj = b & (half - 1), blk = b / half;
+            const int i0 = blk * 2 * half + jj, i1 = i0 + half;
+            fr_t u = x[i0], v = x[i1];
+            x[i0] = u + v;
+            fr_t d = u - v;
+            const int e = jj << s;
+            x[i1] = e ? d * c.w[e] : d;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int r = ((k & 1) << 2) | (k & 2) | ((k & 4) >> 2);  // X[k] sits at the bit-reversed position
+        store_fr(&t_out[(size_t)k * n + m], x[r] * c.scale[k]);
+    }
+}
+void ntt_combine8(const NttTables& T, const fr_t* PJ, fr_t* t_out, int logn, cudaStream_t st) {
+    const size_t n = (size_t)1 << logn;
+    Combine8Consts c;
+    c.w[0] = fr_t::one();
+    for (int e = 1; e < 4; e++) c.w[e] = c.w[e - 1] * T.omega_inv[3];
+    // g^(-N): 7^-1 squared logn times
+    fr_t gin = fr_generator_host().inverse();
+    for (int k = 0; k < logn; k++) gin = gin.sqr();
+    fr_t sc = T.ninv[3];
+    for (int k = 0; k < 8; k++) {
+        c.scale[k] = sc;
+        sc = sc * gin;
+    }
+    ZP_LAUNCH(ntt_combine8_kernel, dim3((unsigned)((n + 127) / 128)), dim3(128), 0, st, PJ, t_out, n, c);
+}
+
+}  // namespace zp
+
 // =====================================================================================================
 // Four-step NTT over G ranks.  N = G*M, m = M/G.  With n = n2*G + n1 and k = k1*M + k2:
 //     X[k1*M + k2] = sum_{n1} w_G^{n1 k1} * ( w_N^{n1 k2} * sum_{n2} w_M^{n2 k2} x[n2*G + n1] )

@@ -48,6 +48,15 @@ struct NttScratch {
 void ntt_run(const NttTables& T, NttScratch& S, NttKind kind, int logn, const fr_t* in, size_t n_in, fr_t* out,
              cudaStream_t st);
 
+// Coset-by-coset view of the size-8N extended domain (used when the quotient round is sharded over GPUs): the points
+// g w_8N^(8 i + j), i < N, form the coset (g w_8N^j) H_N, so the evaluations of a degree < N polynomial on it are ONE size-N
+// coset NTT of the coefficients pre-multiplied by w_8N^(j m).
+//   ntt_coset_shift : out[m] = in[m] * w_{2^logn_big}^(+- j m), m < n   (in == out allowed)
+//   ntt_combine8    : given P_j = size-N coset-iNTT over coset j of the quotient values (j < 8, PJ[j * N + m]), writes the
+//                     8N coefficients t[m' * N + m] = g^(-N m') / 8 * sum_j w_8^(-j m') P_j[m]  (the split t_1 .. t_8)
+void ntt_coset_shift(const NttTables& T, const fr_t* in, fr_t* out, size_t n, int logn_big, int j, bool inverse, cudaStream_t st);
+void ntt_combine8(const NttTables& T, const fr_t* PJ, fr_t* t_out, int logn, cudaStream_t st);
+
 // host-side field helpers shared by the driver
 fr_t fr_two_adic_root_host();
 fr_t fr_generator_host();

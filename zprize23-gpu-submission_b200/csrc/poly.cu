@@ -484,16 +484,22 @@ bool combine_split(CombineSplitScratch& S, const fr_t* t, const fr_t* f, size_t 
 template <bool CUSTOM, bool LOOKUP>
 __global__ void __launch_bounds__(128) quotient_kernel(QuotientArgs a) {
     const size_t n8 = (size_t)1 << (a.logn + 3);
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.i_count) return;
-    i += a.i_begin;
-    size_t nx = (i + 8) & (n8 - 1);
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.i_count) return;
+    t += a.i_begin;
+    // i: natural index on the 8N domain (prover-key streams, l1, x, Z_H); wi / nx: index of this point and of the "next"
+    // point (omega * x) in the wire-like arrays
+    size_t i = t, wi = t, nx = (t + 8) & (n8 - 1);
+    if (a.coset_j >= 0) {
+        i = 8 * t + (size_t)a.coset_j;
+        nx = (t + 1) & ((n8 >> 3) - 1);
+    }
     const fr_t one = fr_t::one();
     GateVals<fr_t> g;
-    g.a = load_fr(&a.w[0][i]);
-    g.b = load_fr(&a.w[1][i]);
-    g.c = load_fr(&a.w[2][i]);
-    g.d = load_fr(&a.w[3][i]);
+    g.a = load_fr(&a.w[0][wi]);
+    g.b = load_fr(&a.w[1][wi]);
+    g.c = load_fr(&a.w[2][wi]);
+    g.d = load_fr(&a.w[3][wi]);
 
     // ---- arithmetic widget (arithmetic.rs:61-79)
     fr_t arith = load_fr(&a.sel[5][i]);  // q_c
@@ -525,27 +531,26 @@ __global__ void __launch_bounds__(128) quotient_kernel(QuotientArgs a) {
     {
         uint32_t ex = (uint32_t)i << (NTT_LMAX - (a.logn + 3));
         uint32_t lo = ex & ((1u << NTT_LO_BITS) - 1), hi = ex >> NTT_LO_BITS;
-        fr_t x = a.g * load_fr(&a.w_hi[hi]);
-        if (lo) x = x * load_fr(&a.w_lo[lo]);
-        fr_t bx = a.beta * x;
+        fr_t bx = a.beta_g * load_fr(&a.w_hi[hi]);  // beta * x, beta * g folded on the host
+        if (lo) bx = bx * load_fr(&a.w_lo[lo]);
         fr_t b2 = bx.dbl(), b4 = b2.dbl(), b8 = b4.dbl(), b16 = b8.dbl();
         fr_t ag = g.a + a.gamma, bg = g.b + a.gamma, cg = g.c + a.gamma, dg = g.d + a.gamma;
-        fr_t zi = load_fr(&a.z[i]), zn = load_fr(&a.z[nx]);
-        fr_t id = (ag + bx) * (bg + (b8 - bx)) * (cg + (b8 + b4 + bx)) * (dg + (b16 + bx)) * zi * a.alpha;
+        fr_t zi = load_fr(&a.z[wi]), zn = load_fr(&a.z[nx]);
+        fr_t id = (ag + bx) * (bg + (b8 - bx)) * (cg + (b8 + b4 + bx)) * (dg + (b16 + bx)) * zi;
         fr_t cp = (ag + a.beta * load_fr(&a.sigma[0][i])) * (bg + a.beta * load_fr(&a.sigma[1][i])) *
-                  (cg + a.beta * load_fr(&a.sigma[2][i])) * (dg + a.beta * load_fr(&a.sigma[3][i])) * zn * a.alpha;
+                  (cg + a.beta * load_fr(&a.sigma[2][i])) * (dg + a.beta * load_fr(&a.sigma[3][i])) * zn;
         fr_t l1a = load_fr(&a.l1[i]) * a.alpha_sq;
-        total = total + (id - cp) + (zi - one) * l1a;
+        total = total + (id - cp) * a.alpha + (zi - one) * l1a;
     }
 
     // ---- lookup widget (lookup.rs:98-152)
     if (LOOKUP) {
         fr_t lsep_sq = a.lookup_sep.sqr(), lsep_cu = lsep_sq * a.lookup_sep;
         fr_t opd = a.delta + one, eopd = a.epsilon * opd;
-        fr_t fi = load_fr(&a.f[i]);
-        fr_t ti = load_fr(&a.table[i]), tn = load_fr(&a.table[nx]);
-        fr_t h1i = load_fr(&a.h1[i]), h1n = load_fr(&a.h1[nx]), h2i = load_fr(&a.h2[i]);
-        fr_t z2i = load_fr(&a.z2[i]), z2n = load_fr(&a.z2[nx]);
+        fr_t fi = load_fr(&a.f[wi]);
+        fr_t ti = load_fr(&a.table[wi]), tn = load_fr(&a.table[nx]);
+        fr_t h1i = load_fr(&a.h1[wi]), h1n = load_fr(&a.h1[nx]), h2i = load_fr(&a.h2[wi]);
+        fr_t z2i = load_fr(&a.z2[wi]), z2n = load_fr(&a.z2[nx]);
         fr_t la = fr_t::zero();
         if (a.sel[14]) la = load_fr(&a.sel[14][i]) * (lc4(g.a, g.b, g.c, g.d, a.zeta) - fi) * a.lookup_sep;
         fr_t lb = z2i * opd * (a.epsilon + fi) * (eopd + ti + a.delta * tn) * lsep_sq;
@@ -553,7 +558,7 @@ __global__ void __launch_bounds__(128) quotient_kernel(QuotientArgs a) {
         fr_t ld = (z2i - one) * load_fr(&a.l1[i]) * lsep_cu;
         total = total + la + lb - lcv + ld;
     }
-    store_fr(&a.out[i], total * a.vh_inv[i & 7]);
+    store_fr(&a.out[wi], total * a.vh_inv[i & 7]);
 }
 
 void quotient_evals(const QuotientArgs& a, cudaStream_t st) {

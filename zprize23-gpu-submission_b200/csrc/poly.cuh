@@ -71,9 +71,13 @@ struct QuotientArgs {
     fr_t vh_inv[8];           // 1 / (g^N w8^k - 1)
     fr_t coeff_d;             // JubJub d
     const fr_t *w_lo, *w_hi;  // omega tables (for x = g * omega_8N^i)
-    fr_t g;                   // coset generator 7
+    fr_t beta_g;              // beta * 7 (coset generator folded into the permutation challenge)
     fr_t* out;
     size_t i_begin, i_count;  // index range of the coset handled by this launch (whole coset: 0, 8N)
+    // coset_j >= 0: one size-N coset of the extended domain (points g w_8N^(8 t + coset_j), t < N; i_begin = 0, i_count = N):
+    // w / z / z2 / f / table / h1 / h2 and out are COMPACT arrays indexed by t ("next" = t + 1), the prover-key streams and
+    // l1 stay in natural 8N order and are read at 8 t + coset_j.  -1: the whole 8N domain in natural order.
+    int coset_j;
 };
 void quotient_evals(const QuotientArgs& a, cudaStream_t st);
 

@@ -567,9 +567,13 @@ void Prover::prove_resident(ProofC* out) {
     Fr coeff_d;
     memcpy(coeff_d.v, JUBJUB_D, 32);
     {
-        // the 8N coset NTTs of this round are independent: with a device broadcast hook they are dealt round-robin
-        // to the ranks and the finished 1 GiB arrays are exchanged over NVLink; otherwise every rank computes all
-        const bool dist = shard_world > 1 && dev_bcast != nullptr && (n8 % (size_t)shard_world) == 0;
+        // Multi-GPU (device broadcast hook set, world divides 8): the extended domain g H_8N is the union of the 8 cosets
+        // (g w_8N^j) H_N; rank r owns 8 / world of them and does everything of this round on its cosets only — size-N coset
+        // NTTs of the inputs, the fused quotient pass, the size-N coset iNTT — then the per-coset coefficient vectors P_j are
+        // exchanged (1 GiB in total at N = 2^22) and every rank finishes with the size-8 DFT across cosets (ntt_combine8).
+        // Single GPU: the five (ten with lookups) 8N coset NTTs, one quotient pass, one 8N coset iNTT.
+        const bool dist = shard_world > 1 && dev_bcast != nullptr && (8 % shard_world) == 0;
+        const int cpr = dist ? 8 / shard_world : 0;  // cosets per rank
         struct Job { const fr_t* in; fr_t* out; };
         std::vector<Job> jobs;
         for (int k = 0; k < 4; k++) jobs.push_back({w_poly[k].p, w8[k].p});
@@ -582,12 +586,22 @@ void Prover::prove_resident(ProofC* out) {
             jobs.push_back({h2_poly.p, h28.p});
         }
         { Scope s(CAT_NTT);
-          for (size_t k = 0; k < jobs.size(); k++)
-              if (!dist || (int)(k % shard_world) == shard_rank) ntt_run(T, NS, NTT_COSET_FWD, logn + 3, jobs[k].in, n, jobs[k].out, st);
-          if (dist)
+          if (!dist) {
+              for (size_t k = 0; k < jobs.size(); k++) ntt_run(T, NS, NTT_COSET_FWD, logn + 3, jobs[k].in, n, jobs[k].out, st);
+          } else {
+              if (cs_tmp.n < n) cs_tmp.alloc(n);
+              if (pj8.n < n8) pj8.alloc(n8);
               for (size_t k = 0; k < jobs.size(); k++)
-                  if (dev_bcast(dev_bcast_user, jobs[k].out, n8 * sizeof(fr_t), (int)(k % shard_world)) != 0)
-                      throw std::runtime_error("device broadcast of a coset NTT failed");
+                  for (int c = 0; c < cpr; c++) {  // compact evaluations on coset j at jobs[k].out + c * N
+                      const int j = shard_rank * cpr + c;
+                      const fr_t* src = jobs[k].in;
+                      if (j) {
+                          ntt_coset_shift(T, jobs[k].in, cs_tmp.p, n, logn + 3, j, false, st);
+                          src = cs_tmp.p;
+                      }
+                      ntt_run(T, NS, NTT_COSET_FWD, logn, src, n, jobs[k].out + (size_t)c * n, st);
+                  }
+          }
         }
         QuotientArgs qa;
         qa.logn = logn;
@@ -607,30 +621,51 @@ void Prover::prove_resident(ProofC* out) {
         qa.var_sep = D(var_sep); qa.lookup_sep = D(lookup_sep);
         // Z_H on the coset: g^N * w8^k - 1 (preprocess.rs:498-520), inverted once per residue
         Fr g = H(fr_generator_host());
-        Fr gn = g.pow_u64(n), w8 = H(T.omega[3]), p = gn;
+        Fr gn = g.pow_u64(n), om8 = H(T.omega[3]), p = gn;
         for (int k = 0; k < 8; k++) {
             qa.vh_inv[k] = D((p - Fr::one()).inverse());
-            p = p * w8;
+            p = p * om8;
         }
         qa.coeff_d = D(coeff_d);
         qa.w_lo = T.w_lo.p;
         qa.w_hi = T.w_hi.p;
-        qa.g = fr_generator_host();
+        qa.beta_g = D(beta * g);
         qa.out = quot.p;
         qa.i_begin = 0;
         qa.i_count = n8;
-        if (dist) {  // each rank evaluates its slice of the coset, slices are broadcast to everybody
-            qa.i_count = n8 / shard_world;
-            qa.i_begin = qa.i_count * shard_rank;
-        }
-        { Scope s(CAT_QUOT);
-          quotient_evals(qa, st);
-          if (dist)
+        qa.coset_j = -1;
+        if (!dist) {
+            { Scope s(CAT_QUOT); quotient_evals(qa, st); }
+            { Scope s(CAT_NTT); ntt_run(T, NS, NTT_COSET_INV, logn + 3, quot.p, n8, t_poly.p, st); }
+        } else {
+            for (int c = 0; c < cpr; c++) {
+                const int j = shard_rank * cpr + c;
+                QuotientArgs qc = qa;
+                const size_t off = (size_t)c * n;
+                for (int k = 0; k < 4; k++) qc.w[k] = w8[k].p + off;
+                qc.z = z8.p + off;
+                if (lookup_on) {
+                    qc.z2 = z28.p + off;
+                    qc.f = f8.p + off; qc.table = tb8.p + off; qc.h1 = h18.p + off; qc.h2 = h28.p + off;
+                }
+                qc.out = quot.p + off;
+                qc.i_count = n;
+                qc.coset_j = j;
+                { Scope s(CAT_QUOT); quotient_evals(qc, st); }
+                { Scope s(CAT_NTT);
+                  // P_j = coefficients of the quotient restricted to coset j: iNTT_N, * 7^-m (coset iNTT), * w_8N^(-j m)
+                  fr_t* pj = pj8.p + (size_t)j * n;
+                  ntt_run(T, NS, NTT_COSET_INV, logn, quot.p + off, n, pj, st);
+                  if (j) ntt_coset_shift(T, pj, pj, n, logn + 3, j, true, st);
+                }
+            }
+            { Scope s(CAT_NTT);
               for (int r = 0; r < shard_world; r++)
-                  if (dev_bcast(dev_bcast_user, quot.p + (size_t)r * qa.i_count, qa.i_count * sizeof(fr_t), r) != 0)
-                      throw std::runtime_error("device broadcast of a quotient slice failed");
+                  if (dev_bcast(dev_bcast_user, pj8.p + (size_t)r * cpr * n, (size_t)cpr * n * sizeof(fr_t), r) != 0)
+                      throw std::runtime_error("device broadcast of the per-coset quotient coefficients failed");
+              ntt_combine8(T, pj8.p, t_poly.p, logn, st);
+            }
         }
-        { Scope s(CAT_NTT); ntt_run(T, NS, NTT_COSET_INV, logn + 3, quot.p, n8, t_poly.p, st); }
     }
     static const char* tl[8] = {"t_1", "t_2", "t_3", "t_4", "t_5", "t_6", "t_7", "t_8"};
     bool t_zero[8];

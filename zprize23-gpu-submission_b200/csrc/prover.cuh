@@ -53,6 +53,7 @@ struct Prover {
     DevBuf<fr_t> z_poly, z8, z2_poly, z28;
     DevBuf<fr_t> t_ev, f_ev, h1_ev, h2_ev, table_poly, f_poly, h1_poly, h2_poly, tb8, f8, h18, h28;
     DevBuf<fr_t> quot, t_poly;
+    DevBuf<fr_t> cs_tmp, pj8;        // multi-GPU quotient round: shifted coefficients (N), per-coset quotient coefficients (8N)
     DevBuf<fr_t> num, den, lin, comb, wit, wit2;
     double last_ms[5] = {0, 0, 0, 0, 0};
     // witness currently resident in w_ev / qlk_ev (set by upload_witness)

@@ -155,6 +155,7 @@ def load_library(path=None):
         "zp_prover_set_device_broadcast": (ci, [vp, DEV_BCAST_FN, vp]),
         "zp_ntt_host": (ci, [vp, ci, ci, u64p, u64p]),
         "zp_msm_host": (ci, [vp, u64p, cs, u64p]),
+        "zp_msm_batch_host": (ci, [vp, u64p, ci, cs, u64p]),
         "zp_ntt_sharded_host": (ci, [vp, ci, ci, ci, ci, u64p, u64p, DEV_A2A_FN, vp]),
         "zp_bench_ntt_sharded": (ci, [vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, DEV_A2A_FN, vp, dp]),
         "zp_msm_points_host": (ci, [vp, u64p, u64p, cs, ci, u64p]),
@@ -186,7 +187,7 @@ EXPORTED_SYMBOLS = ["gen_proof", "zp_proof_serialize", "zp_proof_deserialize", "
                     "zp_prover_destroy", "zp_prover_set_label", "zp_profiler_range", "zp_prover_set_stream", "zp_prover_load_srs", "zp_prover_generate_srs",
                     "zp_prover_read_srs", "zp_prover_load_pk", "zp_prover_preprocess", "zp_prover_verifier_key",
                     "zp_prover_prove", "zp_prover_last_timing", "zp_prover_upload_witness", "zp_prover_prove_resident",
-                    "zp_prover_collect_msm_stats", "zp_prover_msm_stats", "zp_prover_set_shard", "zp_prover_set_device_broadcast", "zp_ntt_host", "zp_ntt_sharded_host", "zp_bench_ntt_sharded", "zp_msm_host", "zp_msm_points_host",
+                    "zp_prover_collect_msm_stats", "zp_prover_msm_stats", "zp_prover_set_shard", "zp_prover_set_device_broadcast", "zp_ntt_host", "zp_ntt_sharded_host", "zp_bench_ntt_sharded", "zp_msm_host", "zp_msm_batch_host", "zp_msm_points_host",
                     "zp_poly_eval_host", "zp_poly_divide_host", "zp_prefix_product_host", "zp_combine_split_host", "zp_bench_alloc",
                     "zp_bench_upload", "zp_bench_download", "zp_bench_ntt", "zp_bench_msm", "zp_bench_msm_batch", "zp_bench_msm_breakdown",
                     "zp_bench_int_pipe"]
@@ -405,6 +406,14 @@ class ProverContext:
     def msm(self, scalars):
         out = np.zeros(12, dtype=np.uint64)
         self._ck(self.lib.zp_msm_host(self.h, as_u64p(scalars), scalars.shape[0], as_u64p(out)))
+        return out
+
+    def msm_batch(self, scalars):
+        """scalars: (k, n, 4) uint64, k <= 8 -> (k, 12) affine points; one MSM pipeline for all k members."""
+        scalars = np.ascontiguousarray(scalars)
+        k, n = scalars.shape[0], scalars.shape[1]
+        out = np.zeros((k, 12), dtype=np.uint64)
+        self._ck(self.lib.zp_msm_batch_host(self.h, as_u64p(scalars), k, n, as_u64p(out)))
         return out
 
     def msm_points(self, points, scalars, window_bits=0):
