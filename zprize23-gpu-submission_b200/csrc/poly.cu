@@ -491,8 +491,10 @@ __global__ void __launch_bounds__(128) quotient_kernel(QuotientArgs a) {
     // point (omega * x) in the wire-like arrays
     size_t i = t, wi = t, nx = (t + 8) & (n8 - 1);
     if (a.coset_j >= 0) {
-        i = 8 * t + (size_t)a.coset_j;
-        nx = (t + 1) & ((n8 >> 3) - 1);
+        const size_t nn = n8 >> 3, c = t & (((size_t)1 << a.coset_lc) - 1), tt = t >> a.coset_lc;
+        i = 8 * tt + (size_t)a.coset_j + c;
+        wi = c * nn + tt;
+        nx = c * nn + ((tt + 1) & (nn - 1));
     }
     const fr_t one = fr_t::one();
     GateVals<fr_t> g;

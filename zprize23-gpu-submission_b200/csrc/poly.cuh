@@ -74,10 +74,11 @@ struct QuotientArgs {
     fr_t beta_g;              // beta * 7 (coset generator folded into the permutation challenge)
     fr_t* out;
     size_t i_begin, i_count;  // index range of the coset handled by this launch (whole coset: 0, 8N)
-    // coset_j >= 0: one size-N coset of the extended domain (points g w_8N^(8 t + coset_j), t < N; i_begin = 0, i_count = N):
-    // w / z / z2 / f / table / h1 / h2 and out are COMPACT arrays indexed by t ("next" = t + 1), the prover-key streams and
-    // l1 stay in natural 8N order and are read at 8 t + coset_j.  -1: the whole 8N domain in natural order.
-    int coset_j;
+    // coset_j >= 0: 2^coset_lc consecutive size-N cosets of the extended domain, coset_j + c (points g w_8N^(8 t + coset_j + c),
+    // t < N; i_begin = 0, i_count = N << coset_lc).  w / z / z2 / f / table / h1 / h2 and out are COMPACT arrays indexed by
+    // c * N + t ("next" = t + 1 inside the coset); the prover-key streams and l1 stay in natural 8N order and are read at
+    // 8 t + coset_j + c, so neighbouring threads (c fastest) read neighbouring elements.  -1: the whole 8N domain, natural order.
+    int coset_j, coset_lc;
 };
 void quotient_evals(const QuotientArgs& a, cudaStream_t st);
 

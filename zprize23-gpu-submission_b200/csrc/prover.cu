@@ -634,30 +634,26 @@ void Prover::prove_resident(ProofC* out) {
         qa.i_begin = 0;
         qa.i_count = n8;
         qa.coset_j = -1;
+        qa.coset_lc = 0;
         if (!dist) {
             { Scope s(CAT_QUOT); quotient_evals(qa, st); }
             { Scope s(CAT_NTT); ntt_run(T, NS, NTT_COSET_INV, logn + 3, quot.p, n8, t_poly.p, st); }
         } else {
+            {   // one fused pass over this rank's cosets (compact arrays in, compact quotient values out)
+                QuotientArgs qc = qa;
+                qc.i_count = (size_t)cpr * n;
+                qc.coset_j = shard_rank * cpr;
+                qc.coset_lc = ilog2((size_t)cpr);
+                Scope s(CAT_QUOT);
+                quotient_evals(qc, st);
+            }
             for (int c = 0; c < cpr; c++) {
                 const int j = shard_rank * cpr + c;
-                QuotientArgs qc = qa;
-                const size_t off = (size_t)c * n;
-                for (int k = 0; k < 4; k++) qc.w[k] = w8[k].p + off;
-                qc.z = z8.p + off;
-                if (lookup_on) {
-                    qc.z2 = z28.p + off;
-                    qc.f = f8.p + off; qc.table = tb8.p + off; qc.h1 = h18.p + off; qc.h2 = h28.p + off;
-                }
-                qc.out = quot.p + off;
-                qc.i_count = n;
-                qc.coset_j = j;
-                { Scope s(CAT_QUOT); quotient_evals(qc, st); }
-                { Scope s(CAT_NTT);
-                  // P_j = coefficients of the quotient restricted to coset j: iNTT_N, * 7^-m (coset iNTT), * w_8N^(-j m)
-                  fr_t* pj = pj8.p + (size_t)j * n;
-                  ntt_run(T, NS, NTT_COSET_INV, logn, quot.p + off, n, pj, st);
-                  if (j) ntt_coset_shift(T, pj, pj, n, logn + 3, j, true, st);
-                }
+                Scope s(CAT_NTT);
+                // P_j = coefficients of the quotient restricted to coset j: iNTT_N, * 7^-m (coset iNTT), * w_8N^(-j m)
+                fr_t* pj = pj8.p + (size_t)j * n;
+                ntt_run(T, NS, NTT_COSET_INV, logn, quot.p + (size_t)c * n, n, pj, st);
+                if (j) ntt_coset_shift(T, pj, pj, n, logn + 3, j, true, st);
             }
             { Scope s(CAT_NTT);
               for (int r = 0; r < shard_world; r++)
