@@ -216,8 +216,8 @@ def main():
     sampler.start()
     t0 = time.perf_counter()
     e0.record(stream)
-    acc_ms = acc_mads = exec_mads = 0.0
-    acc_launch = acc_commits = 0
+    acc_ms = acc_mads = exec_mads = down_ms = down_pairs = 0.0
+    acc_launch = acc_commits = down_launch = 0
     phase = {"ntt_ms": 0.0, "msm_ms": 0.0, "quotient_ms": 0.0, "other_ms": 0.0}
     for _ in range(args.steps):
         words = ctx.prove_resident().to_words()
@@ -227,6 +227,9 @@ def main():
         acc_launch += st["launches"]
         exec_mads += st["executed_mads"]
         acc_commits += st["commitments"]
+        down_ms += st["down0_ms"]
+        down_pairs += st["down0_pairs"]
+        down_launch += st["down0_launches"]
         tm = ctx.last_timing()
         for k in phase:
             phase[k] += tm[k] / args.steps
@@ -267,8 +270,11 @@ def main():
         return
 
     # ---- roofline of the dominant kernel (MSM bucket accumulation, integer-pipe bound) + the NTT (HBM)
-    achieved = acc_mads / (acc_ms * 1e-3) / 1e12 if acc_ms > 0 else None  # T mad/s, SURVEY 8d count (XYZZ: 10 products / entry)
-    executed = exec_mads / (acc_ms * 1e-3) / 1e12 if acc_ms > 0 else None  # T mad/s actually issued (batch-affine: ~6.2 / entry)
+    # ---- roofline of the dominant kernel: ba_down0_kernel (batch-affine bucket additions of the MSM, integer-pipe bound).
+    # Algorithmic work per affine addition it performs: 3 Fq products for the chord (lambda, lambda^2, y3) + 15/8 for
+    # recovering 1/(x2-x1) from the shared inversion inside a 16-slot leaf group = 4.875 * 588 multiply-adds.
+    DOWN0_MADS_PER_ADD = (3.0 + 15.0 / 8.0) * 588.0
+    down_ach = down_pairs * DOWN0_MADS_PER_ADD / (down_ms * 1e-3) / 1e12 if down_ms > 0 else None
     traffic = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
@@ -276,18 +282,28 @@ def main():
             traffic = tj["ba_down0_kernel"]["traffic_bytes_per_launch"]  # bytes per launch, one ncu --set full capture
     except Exception:  # noqa: BLE001
         pass
-    roofline = {"bound": "int32-mad",
-                "kernel": "MSM bucket accumulation: ba_up0_kernel + ba_down0_kernel (batch-affine rounds) + msm_accumulate_kernel",
-                "achieved": achieved, "peak": int_peak,
-                "unit": "Tmad/s", "frac": (achieved / int_peak) if achieved and int_peak else None,
-                "executed_achieved": executed, "executed_frac": (executed / int_peak) if executed and int_peak else None,
-                "traffic": traffic, "traffic_unit": "bytes per launch of ba_down0_kernel round 1 (dram read + write, ncu)",
-                "peak_source": "in-run dependent-free mad.lo.u32 microbenchmark (SURVEY 8d); achieved = algorithmic ops 10*588*M*W / "
-                               "device time of the stage; executed_* counts the multiply-adds really issued (a batch-affine "
-                               "addition is ~6.2 Fq products instead of the 10 of the XYZZ formula 8d assumes)",
-                "launches": acc_launch, "commitments": acc_commits, "avg_launch_ms": acc_ms / max(acc_launch, 1),
-                "avg_ms_per_commitment": acc_ms / max(acc_commits, 1),
-                "share_of_step": acc_ms / args.steps / step_ms}
+    roofline = {"bound": "int32-mad", "kernel": "ba_down0_kernel",
+                "achieved": down_ach, "peak": int_peak, "unit": "Tmad/s",
+                "frac": (down_ach / int_peak) if down_ach and int_peak else None,
+                "traffic": traffic,
+                "traffic_unit": "bytes (dram read + write, ncu --set full) of the largest launch: round 1 of the 4-member wire batch",
+                "peak_source": "in-run dependent-free mad.lo.u32 microbenchmark (SURVEY 8d)",
+                "algorithmic_ops": "4.875 * 588 multiply-adds per affine bucket addition x additions counted on the device",
+                "launches": down_launch, "avg_launch_ms": down_ms / max(down_launch, 1),
+                "share_of_step": down_ms / args.steps / step_ms}
+    # the whole bucket-accumulation stage of the MSM against SURVEY 8d's algorithmic count 10*588*M*W (an XYZZ mixed addition
+    # per bucket entry).  The batch-affine rounds do the same additions with ~6.2 products, so `achieved` may exceed the
+    # pipe's peak; `executed_*` counts the multiply-adds really issued.
+    achieved = acc_mads / (acc_ms * 1e-3) / 1e12 if acc_ms > 0 else None
+    executed = exec_mads / (acc_ms * 1e-3) / 1e12 if acc_ms > 0 else None
+    roofline_msm = {"bound": "int32-mad",
+                    "kernel": "MSM bucket accumulation stage: ba_up0_kernel + ba_down0_kernel + inversion tree (4 rounds) + msm_accumulate_kernel",
+                    "achieved": achieved, "peak": int_peak, "unit": "Tmad/s",
+                    "frac": (achieved / int_peak) if achieved and int_peak else None,
+                    "executed_achieved": executed, "executed_frac": (executed / int_peak) if executed and int_peak else None,
+                    "algorithmic_ops": "10 * 588 * M * W (SURVEY 8d)",
+                    "pipelines": acc_launch, "commitments": acc_commits, "avg_ms_per_commitment": acc_ms / max(acc_commits, 1),
+                    "share_of_step": acc_ms / args.steps / step_ms}
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -330,6 +346,7 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
+        "roofline_msm_stage": roofline_msm,
         "roofline_ntt": roofline_ntt,
         "phase_ms_per_step": phase,
         "timing": {"cuda_event_ms_per_step": dev_ms / args.steps, "wall_ms_per_step": wall_ms / args.steps},

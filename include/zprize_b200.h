@@ -153,9 +153,10 @@ int zp_prover_prove_resident(zp_prover* p, ProofC* out);
  * proof read out4 = { sum of kernel ms, launches, algorithmic 32-bit multiply-adds (10*588*M*W),
  * sum of all MSM kernel ms }. */
 int zp_prover_collect_msm_stats(zp_prover* p, int enable);
-/* out6: bucket-accumulation ms (batch-affine rounds + XYZZ accumulate), MSM pipelines launched, algorithmic mads
- * (10*588*M*W), all MSM stages ms, mads actually issued (estimate), commitments produced */
-int zp_prover_msm_stats(zp_prover* p, double* out6);
+/* out9: bucket-accumulation ms (batch-affine rounds + XYZZ accumulate), MSM pipelines launched, algorithmic mads
+ * (10*588*M*W), all MSM stages ms, mads actually issued (estimate), commitments produced, and for the dominant kernel
+ * ba_down0_kernel: device ms, affine additions performed, launches */
+int zp_prover_msm_stats(zp_prover* p, double* out9);
 /* Multi-GPU sharding of the commitments (one process per GPU, every rank holds the same key and witness):
  * rank r computes each MSM over points [r*ceil(n/world), (r+1)*ceil(n/world)) only and the partial sums
  * are exchanged with `allgather(user, send, recv, bytes_per_rank)` — recv holds world * bytes_per_rank

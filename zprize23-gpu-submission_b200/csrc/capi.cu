@@ -100,15 +100,18 @@ int zp_prover_prove(zp_prover* p, const CircuitC* c, ProofC* out) { return guard
 int zp_prover_upload_witness(zp_prover* p, const CircuitC* c) { return guard([&] { P(p)->upload_witness(*c); }); }
 int zp_prover_prove_resident(zp_prover* p, ProofC* out) { return guard([&] { P(p)->prove_resident(out); }); }
 int zp_prover_collect_msm_stats(zp_prover* p, int enable) { return guard([&] { P(p)->collect_msm_stats = enable != 0; }); }
-int zp_prover_msm_stats(zp_prover* p, double* out6) {
+int zp_prover_msm_stats(zp_prover* p, double* out9) {
     return guard([&] {
         Prover* pr = P(p);
-        out6[0] = pr->msm_acc_ms;
-        out6[1] = pr->msm_launches;
-        out6[2] = pr->msm_mads;
-        out6[3] = pr->msm_all_ms;
-        out6[4] = pr->msm_exec_mads;
-        out6[5] = pr->msm_count;
+        out9[0] = pr->msm_acc_ms;
+        out9[1] = pr->msm_launches;
+        out9[2] = pr->msm_mads;
+        out9[3] = pr->msm_all_ms;
+        out9[4] = pr->msm_exec_mads;
+        out9[5] = pr->msm_count;
+        out9[6] = pr->msm_down0_ms;
+        out9[7] = pr->msm_down0_pairs;
+        out9[8] = pr->msm_down0_launches;
     });
 }
 int zp_prover_set_shard(zp_prover* p, int rank, int world, zp_allgather_fn fn, void* user) {

@@ -517,6 +517,11 @@ static void msm_launch_impl(MsmWorkspace& ws, const MsmConfig& cfg, const affine
             if (ws.ba_rs[k].n < wb + 1) ws.ba_rs[k].alloc(wb + 1);
         if (!ws.ba_flag.p) ws.ba_flag.alloc(2);
         ZP_CUDA(cudaMemsetAsync(ws.ba_flag.p, 0, 2 * sizeof(uint32_t), st));
+        const bool stats = ws.timing && rounds <= MsmWorkspace::BA_MAX_ROUNDS;
+        if (stats) {
+            if (!ws.ba_pairs.p) ws.ba_pairs.alloc(1);
+            ZP_CUDA(cudaMemsetAsync(ws.ba_pairs.p, 0, sizeof(unsigned long long), st));
+        }
         for (int r = 0; r < rounds; r++) {
             size_t cap = est / 2 + wb;
             uint32_t* rs = ws.ba_rs[r & 1].p;
@@ -526,12 +531,20 @@ static void msm_launch_impl(MsmWorkspace& ws, const MsmConfig& cfg, const affine
             ZP_LAUNCH(ba_pair_count_kernel, dim3((unsigned)((wb + 255) / 256)), dim3(256), 0, st, run_begin, run_end, wb, ws.ba_cnt.p);
             msm_scan(ws.ba_cnt.p, rs, wb, ws.tile_sum.p, st);
             ZP_LAUNCH(ba_slots_kernel, dim3((unsigned)((wb * 32 + 255) / 256)), dim3(256), 0, st, run_begin, run_end, rs, wb,
-                      ws.ba_src.p);
+                      ws.ba_src.p, stats ? ws.ba_pairs.p : (unsigned long long*)nullptr);
             ZP_LAUNCH(ba_up0_kernel, dim3(nblk), dim3(BA_T), 0, st, ws.ba_src.p, rs + wb, cap, entries, pts, pstride, ws.ba_pre.p,
                       ws.ba_den.p, ws.ba_flag.p);
             fq_batch_inverse(ws.ba_den.p, m, ws.ba_den.p + m, st);
+            if (stats) {
+                if (!ws.down_ev[2 * r]) {
+                    ZP_CUDA(cudaEventCreate(&ws.down_ev[2 * r]));
+                    ZP_CUDA(cudaEventCreate(&ws.down_ev[2 * r + 1]));
+                }
+                ZP_CUDA(cudaEventRecord(ws.down_ev[2 * r], st));
+            }
             ZP_LAUNCH(ba_down0_kernel, dim3(nblk), dim3(BA_T), 0, st, ws.ba_src.p, rs + wb, cap, entries, pts, pstride, ws.ba_pre.p,
                       ws.ba_den.p, out);
+            if (stats) ZP_CUDA(cudaEventRecord(ws.down_ev[2 * r + 1], st));
             run_begin = rs;
             run_end = rs + 1;
             entries = nullptr;
@@ -581,8 +594,10 @@ static void msm_launch_impl(MsmWorkspace& ws, const MsmConfig& cfg, const affine
     ZP_LAUNCH(msm_fold_kernel, dim3((unsigned)((wb + 3) / 4)), dim3(128), 0, st, ws.segs.p, ws.seg_start.p, wb);
     mark(5);
     const int groups = msm_reduce_groups(cfg), lw2 = msm_reduce_lw2(cfg);
-    ZP_LAUNCH(msm_rowcol_kernel, dim3((unsigned)(nsets * msm_reduce_entries(cfg))), dim3(128), 0, st, ws.segs.p, ws.seg_start.p,
-              cfg.nbuckets, lw2, ws.rowcol.p);
+    // threads per row / column sum: fewer threads = longer serial part but a shorter tree and more resident CTAs
+    static const int rowcol_threads = getenv("ZP_MSM_ROWCOL_THREADS") ? atoi(getenv("ZP_MSM_ROWCOL_THREADS")) : 128;
+    ZP_LAUNCH(msm_rowcol_kernel, dim3((unsigned)(nsets * msm_reduce_entries(cfg))), dim3(rowcol_threads), 0, st, ws.segs.p,
+              ws.seg_start.p, cfg.nbuckets, lw2, ws.rowcol.p);
     ZP_LAUNCH(msm_weighted_kernel, dim3((unsigned)(nsets * groups)), dim3(128), 0, st, ws.rowcol.p, cfg.nbuckets, lw2, groups,
               ws.partial.p);
     ZP_LAUNCH(msm_final_kernel, dim3(nsets), dim3(128), 0, st, ws.partial.p, groups, ws.final_sums.p);
@@ -592,6 +607,8 @@ static void msm_launch_impl(MsmWorkspace& ws, const MsmConfig& cfg, const affine
         // entries the accumulate kernel saw (for the roofline accounting) + the degenerate-pair flag
         ZP_CUDA(cudaMemcpyAsync(&ws.ba_flag_host[1], run_begin + wb, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         ZP_CUDA(cudaMemcpyAsync(&ws.ba_flag_host[0], ws.ba_flag.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        if (ws.timing && ws.ba_pairs.p)
+            ZP_CUDA(cudaMemcpyAsync(&ws.ba_pairs_host, ws.ba_pairs.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     }
     ws.acc_entries = (double)wn;
     ws.ba_rounds_used = rounds > 0 ? rounds : 0;
@@ -625,6 +642,17 @@ std::vector<host::G1> msm_collect_batch(MsmWorkspace& ws, const MsmConfig& cfg, 
             float ms = 0;
             ZP_CUDA(cudaEventElapsedTime(&ms, ws.ev[k], ws.ev[k + 1]));
             ws.last_ms[k] = ms;
+        }
+        ws.down0_ms = ws.down0_pairs = 0;
+        ws.down0_launches = 0;
+        if (ws.ba_used && ws.ba_rounds_used <= MsmWorkspace::BA_MAX_ROUNDS && ws.down_ev[0]) {
+            for (int r = 0; r < ws.ba_rounds_used; r++) {
+                float ms = 0;
+                ZP_CUDA(cudaEventElapsedTime(&ms, ws.down_ev[2 * r], ws.down_ev[2 * r + 1]));
+                ws.down0_ms += ms;
+            }
+            ws.down0_launches = ws.ba_rounds_used;
+            ws.down0_pairs = (double)ws.ba_pairs_host;
         }
     }
     std::vector<host::G1> res(ws.last_nbatch);

@@ -71,6 +71,14 @@ struct MsmWorkspace {
     int last_nbatch = 1;
     size_t last_n = 0;
     int ba_rounds_used = 0;    // batch-affine rounds of the last launch
+    // bench statistics of the dominant kernel (ba_down0_kernel), filled when `timing` is set: device time of its
+    // launches and the affine additions they performed in the last MSM pipeline
+    static const int BA_MAX_ROUNDS = 8;
+    cudaEvent_t down_ev[2 * BA_MAX_ROUNDS] = {};
+    DevBuf<unsigned long long> ba_pairs;
+    unsigned long long ba_pairs_host = 0;
+    double down0_ms = 0, down0_pairs = 0;
+    int down0_launches = 0;
     size_t seg = 0;            // points per work segment (2x the mean bucket load, >= 32)
     size_t max_segs = 0;
     DevBuf<xyzz_t> rowcol;     // [nsets][W1 + W2] row / column sums of the bucket matrix (bucket reduction, step 1)

@@ -335,6 +335,9 @@ std::vector<host::G1> Prover::msm_over_srs_batch(const fr_t* const* scalars_dev,
         msm_exec_mads += 588.0 * (6.2 * (entries - left) + 10.0 * left);
         msm_launches++;
         msm_count += k;
+        msm_down0_ms += MW.down0_ms;
+        msm_down0_pairs += MW.down0_pairs;
+        msm_down0_launches += MW.down0_launches;
     }
     return r;
 }
@@ -443,6 +446,8 @@ void Prover::prove_resident(ProofC* out) {
     const bool lookup_on = wit_lookup_on;
     msm_acc_ms = msm_all_ms = msm_mads = msm_exec_mads = 0;
     msm_launches = msm_count = 0;
+    msm_down0_ms = msm_down0_pairs = 0;
+    msm_down0_launches = 0;
     MW.timing = collect_msm_stats;
     struct TimingOff { MsmWorkspace& w; ~TimingOff() { w.timing = false; } } timing_off{MW};
 

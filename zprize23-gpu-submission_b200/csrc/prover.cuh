@@ -65,6 +65,8 @@ struct Prover {
     bool collect_msm_stats = false;
     double msm_acc_ms = 0, msm_all_ms = 0, msm_mads = 0, msm_exec_mads = 0;
     int msm_launches = 0, msm_count = 0;  // MSM pipelines launched / commitments they produced
+    double msm_down0_ms = 0, msm_down0_pairs = 0;  // ba_down0_kernel: device ms and affine additions over the proof
+    int msm_down0_launches = 0;
 
     // multi-GPU: every rank runs the whole protocol on identical inputs, but each KZG commitment's MSM is
     // sharded by point range; the per-rank partial sums (one XYZZ point, 192 B) are exchanged through the

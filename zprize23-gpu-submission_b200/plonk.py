@@ -332,10 +332,11 @@ class ProverContext:
         self._ck(self.lib.zp_prover_collect_msm_stats(self.h, 1 if enable else 0))
 
     def msm_stats(self):
-        out = (ctypes.c_double * 6)()
+        out = (ctypes.c_double * 9)()
         self._ck(self.lib.zp_prover_msm_stats(self.h, out))
         return {"accumulate_ms": out[0], "launches": int(out[1]), "algorithmic_mads": out[2], "all_kernels_ms": out[3],
-                "executed_mads": out[4], "commitments": int(out[5])}
+                "executed_mads": out[4], "commitments": int(out[5]), "down0_ms": out[6], "down0_pairs": out[7],
+                "down0_launches": int(out[8])}
 
     def set_shard(self, rank, world, allgather):
         """allgather(send_bytes: bytes) -> bytes of world * len(send_bytes) in rank order (e.g. torch.distributed)."""
