@@ -72,11 +72,11 @@ struct MsmWorkspace {
     size_t last_n = 0;
     int ba_rounds_used = 0;    // batch-affine rounds of the last launch
     // bench statistics of the dominant kernel (ba_down0_kernel), filled when `timing` is set: device time of its
-    // launches and the affine additions they performed in the last MSM pipeline
+    // launches and the affine additions they performed in the last MSM pipeline (every round turns a run of len entries
+    // into ceil(len / 2) with floor(len / 2) additions, so additions = entries before the rounds - entries after them)
     static const int BA_MAX_ROUNDS = 8;
     cudaEvent_t down_ev[2 * BA_MAX_ROUNDS] = {};
-    DevBuf<unsigned long long> ba_pairs;
-    unsigned long long ba_pairs_host = 0;
+    uint32_t ba_entries_host = 0;  // bucket entries before the first round
     double down0_ms = 0, down0_pairs = 0;
     int down0_launches = 0;
     size_t seg = 0;            // points per work segment (2x the mean bucket load, >= 32)

@@ -26,13 +26,11 @@ __global__ void __launch_bounds__(256) ba_pair_count_kernel(const uint32_t* __re
 // Slot table: src0[j] = (index of the first point of pair j) << 1 | (the slot is a real pair, not a leftover).
 // One warp per bucket run, lanes over the pairs of the run (coalesced stores; no per-slot search).
 __global__ void __launch_bounds__(256) ba_slots_kernel(const uint32_t* __restrict__ begin, const uint32_t* __restrict__ endp,
-                                                       const uint32_t* __restrict__ rs, size_t nb, uint32_t* __restrict__ src0,
-                                                       unsigned long long* __restrict__ pair_count) {
+                                                       const uint32_t* __restrict__ rs, size_t nb, uint32_t* __restrict__ src0) {
     size_t b = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
     if (b >= nb) return;
     const uint32_t b0 = begin[b], len = endp[b] - b0, o = rs[b], np = (len + 1) >> 1;
-    if (pair_count && lane == 0 && len > 1) atomicAdd(pair_count, (unsigned long long)(len >> 1));  // real additions (bench statistics)
     for (uint32_t t = lane; t < np; t += 32) src0[o + t] = ((b0 + 2 * t) << 1) | (2 * t + 1 < len ? 1u : 0u);
 }
 
