@@ -338,8 +338,10 @@ def main():
         "dtype": "u32-limb Montgomery (BLS12-381 Fr/Fq)", "data": "synthetic",
         "config": {"workload": "Poseidon Merkle tree HEIGHT=%d PLONK gen_proof (cs.n=%d, domain 2^%d, zero lookup table), "
                                "witness seed 42, SRS tau seed 7" % (args.height, oc.cs_n, oc.log_n),
-                   "parallelism": "1 proof over %d GPU(s): MSMs sharded by point range (192-byte partial sums all-gathered per commitment batch); quotient round sharded by the 8 cosets of the extended domain (size-N coset NTTs + fused quotient pass + coset iNTT per rank, per-coset coefficients broadcast over NCCL, size-8 DFT across cosets)"
-                                  "round-robin and quotient pass split by range (NCCL broadcast of finished arrays)" % world,
+                   "parallelism": "1 proof over %d GPU(s): MSMs sharded by point range (192-byte partial sums all-gathered per "
+                                  "commitment batch); quotient round sharded by the 8 cosets of the extended domain (size-N coset "
+                                  "NTTs + fused quotient pass + coset iNTT per rank, per-coset coefficients broadcast over NCCL, "
+                                  "size-8 DFT across cosets)" % world,
                    "l2": "inputs larger than L2 (each polynomial 128 MiB, extended arrays 1 GiB)",
                    "resident": "prover key, SRS, twiddles (and the witness for `value`) in HBM before the timed region"},
         "e2e": {"value": e2e_step_ms / 1e3, "unit": "s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},

@@ -114,7 +114,8 @@ uint64_t zp_launch_count(void);
 /* 1 if a CUDA device is usable */
 int zp_device_available(void);
 
-/* Context for domain size N = 2^log_n on the current CUDA device. NULL on error. */
+/* Context for domain size N = 2^log_n on the current CUDA device. NULL on error.  log_n in [6, 23] for proving (the 8N
+ * extended domain must fit 2^26); log_n in (23, 26] gives an operator-only context (SRS, MSM and NTT entry points). */
 zp_prover* zp_prover_create(int log_n);
 void zp_prover_destroy(zp_prover* p);
 /* Run all work of this context on the caller's CUDA stream (a cudaStream_t, e.g. torch's current stream)

@@ -235,6 +235,23 @@ def test_msm_batch_matches_oracle(pkg, gpu_lib, oracle, logn, k):
     ctx.close()
 
 
+def test_msm_full_size_trapdoor_identity(pkg, gpu_lib, oracle):
+    """BASELINE full sizes through a size-independent property: with the known-trapdoor SRS [tau^i] G,
+    MSM(s) = [sum_i s_i tau^i] G.  2^22 is the HEIGHT=15 commitment (precomputed table, 4 batch-affine rounds, batch of 2);
+    2^24 runs in an operator-only context (no 8N domain)."""
+    for logn, k in [(22, 2), (24, 1)]:
+        n = 1 << logn
+        ctx = pkg.ProverContext(logn, gpu_lib)
+        tau = oracle.random_fr(7, 1)[0]
+        ctx.generate_srs(tau)
+        g = ctx.read_srs(1)[0]
+        sc = np.stack([oracle.random_fr(50 + j, n) for j in range(k)])
+        out = ctx.msm_batch(sc)
+        for j in range(k):
+            assert np.array_equal(out[j], oracle.g1_mul(g, oracle.poly_eval(sc[j], tau))), (logn, j)
+        ctx.close()
+
+
 def test_combine_split_on_device(ctx16, oracle, pkg):
     def small(vals):
         a = np.zeros((len(vals), 4), dtype=np.uint64)

@@ -29,7 +29,7 @@ def main():
     logs = [int(x) for x in args.logs.split(",")]
     lmax = max(logs)
     tau = orc.random_fr(7, 1)[0]
-    n = 1 << min(lmax, 23)
+    n = 1 << min(lmax, 24)
     x = orc.random_fr(2, n)
     if args.dist == "witness":
         rng = np.random.default_rng(3)

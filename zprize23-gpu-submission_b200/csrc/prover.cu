@@ -66,7 +66,9 @@ Prover::Prover(int logn_) : logn(logn_), n((size_t)1 << logn_), n8((size_t)8 << 
     if (pc && pc[0] == '0') use_precomp = false;
     const char* pm = getenv("ZP_MSM_PRECOMP_MIN_LOG");
     if (pm) precomp_min = (size_t)1 << atoi(pm);
-    if (logn < 6 || logn + 3 > NTT_LMAX) throw std::runtime_error("zp_prover_create: log_n must be in [6, 23]");
+    if (logn < 6 || logn > NTT_LMAX) throw std::runtime_error("zp_prover_create: log_n must be in [6, 26]");
+    // proving needs the 8N extended domain (<= 2^26); a larger context serves the SRS / MSM / NTT operator entry points only
+    msm_only = logn + 3 > NTT_LMAX;
 #ifndef ZP_EMU
     // experiment knob: DRAM -> L2 fill granularity hint for the random 96-byte point gathers of the MSM (32 | 64 | 128)
     if (const char* g = getenv("ZP_L2_FETCH")) {
@@ -79,6 +81,10 @@ Prover::Prover(int logn_) : logn(logn_), n((size_t)1 << logn_), n8((size_t)8 << 
     ZP_CUDA(cudaStreamCreate(&st));
     T.init(st);
     PS.init();
+    if (msm_only) {
+        ZP_CUDA(cudaStreamSynchronize(st));
+        return;
+    }
     // L_1 on the coset: coefficients are all 1/N (quotient_poly.rs:346-358)
     l1_coset.alloc(n8);
     DevBuf<fr_t> tmp(n);
@@ -214,6 +220,7 @@ static const uint64_t* pk_eval_ptr(const ProverKeyC& pk, int i) {
 }
 
 void Prover::load_pk(const ProverKeyC& pk, const uint64_t* coeff_len) {
+    if (msm_only) throw std::runtime_error("this context is larger than 2^23: SRS / MSM / NTT operators only, no prover key");
     // reference convention when no lengths are given (gen_proof.cuh:61-62,277-278,319-329)
     static const bool unreadable[PK_COUNT] = {true, false, false, false, false, false, false, false, false, false,
                                               true, true, true, true, true, false, false, false, false};
@@ -259,6 +266,7 @@ void Prover::load_pk(const ProverKeyC& pk, const uint64_t* coeff_len) {
 }
 
 void Prover::preprocess(const uint64_t* const* selector_evals, const uint64_t* const* tables) {
+    if (msm_only) throw std::runtime_error("this context is larger than 2^23: SRS / MSM / NTT operators only, no prover key");
     DevBuf<fr_t> stage(n);
     for (int i = 0; i < PK_COUNT; i++) {
         if (!selector_evals[i]) {

@@ -46,6 +46,7 @@ struct Prover {
     bool table_zero = true;          // all four columns identically zero
     DevBuf<fr_t> l1_coset;           // L_1 on g*H_8N
     bool have_pk = false;
+    bool msm_only = false;           // log_n in (23, 26]: operator entry points only (the 8N domain would exceed 2^26)
 
     // ---- per-proof work buffers (allocated once)
     DevBuf<fr_t> w_ev[4], w_poly[4], w8[4];
