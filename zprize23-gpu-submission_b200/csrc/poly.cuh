@@ -28,7 +28,7 @@ void perm_num_den(fr_t* num, fr_t* den, const fr_t* const w[4], const fr_t* cons
 void lookup_num_den(fr_t* num, fr_t* den, const fr_t* f, const fr_t* t, const fr_t* h1, const fr_t* h2, const fr_t& delta,
                     const fr_t& epsilon, size_t n, cudaStream_t st);
 // den[i] <- num[i] / den[i]   (batched inversion, Montgomery trick per thread)
-void ratio_inplace(const fr_t* num, fr_t* den, size_t n, cudaStream_t st);
+void ratio_inplace(const fr_t* num, fr_t* den, fr_t* scratch /* n elements */, size_t n, cudaStream_t st);
 // out[0] = 1, out[i] = prod_{j<i} r[j]   (the grand product z(X) / z2(X); out may alias r)
 void exclusive_prefix_product(PolyScratch& S, const fr_t* r, fr_t* out, size_t n, cudaStream_t st);
 // p(z) for `count` (polynomial, point) pairs of n coefficients each; results land in host memory

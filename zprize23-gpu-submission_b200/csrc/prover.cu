@@ -534,7 +534,7 @@ void Prover::prove_resident(ProofC* out) {
         const fr_t* sp[4] = {sigma_h[0].p, sigma_h[1].p, sigma_h[2].p, sigma_h[3].p};
         { Scope s(CAT_OTHER);
           perm_num_den(num.p, den.p, wp, sp, D(beta), D(gamma), logn, T, st);
-          ratio_inplace(num.p, den.p, n, st);
+          ratio_inplace(num.p, den.p, comb.p, n, st);
           exclusive_prefix_product(PS, den.p, num.p, n, st); }
         { Scope s(CAT_NTT); ntt_run(T, NS, NTT_INV, logn, num.p, n, z_poly.p, st); }
         Fq x, y; bool inf;
@@ -544,7 +544,7 @@ void Prover::prove_resident(ProofC* out) {
     if (lookup_on) {
         { Scope s(CAT_OTHER);
           lookup_num_den(num.p, den.p, f_ev.p, t_ev.p, h1_ev.p, h2_ev.p, D(delta), D(epsilon), n, st);
-          ratio_inplace(num.p, den.p, n, st);
+          ratio_inplace(num.p, den.p, comb.p, n, st);
           exclusive_prefix_product(PS, den.p, num.p, n, st); }
         { Scope s(CAT_NTT); ntt_run(T, NS, NTT_INV, logn, num.p, n, z2_poly.p, st); }
         commit(z2_poly.p, n, &comm[8]);
