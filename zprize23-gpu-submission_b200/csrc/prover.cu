@@ -421,12 +421,26 @@ void Prover::upload_witness(const CircuitC& c) {
     const size_t cn = (size_t)c.n;
     // ---- 0. witness upload (gen_proof.cuh:11-17, load.cu:311-345)
     ensure_work_buffers(false);
-    const uint64_t* wires[4] = {c.w_l, c.w_r, c.w_o, c.w_4};
-    for (int k = 0; k < 4; k++) {
-        ZP_CUDA(cudaMemcpyAsync(w_ev[k].p, wires[k], cn * sizeof(fr_t), cudaMemcpyHostToDevice, st));
-        if (cn < n) ZP_CUDA(cudaMemsetAsync(w_ev[k].p + cn, 0, (n - cn) * sizeof(fr_t), st));
+    const uint64_t* host[5] = {c.w_l, c.w_r, c.w_o, c.w_4, c.q_lookup};
+    fr_t* dev[5] = {w_ev[0].p, w_ev[1].p, w_ev[2].p, w_ev[3].p, qlk_ev.p};
+    if (shard_world > 1 && dev_bcast) {
+        // every rank holds the same host witness: each one sends only its 1/world slice over PCIe and the slices are
+        // exchanged over NVLink (8 ranks pulling 506 MB each from host memory at once cost 21 ms at HEIGHT=15)
+        const size_t chunk = (cn + shard_world - 1) / shard_world;
+        const size_t lo = std::min(cn, (size_t)shard_rank * chunk), hi = std::min(cn, lo + chunk);
+        for (int k = 0; k < 5; k++)
+            if (hi > lo) ZP_CUDA(cudaMemcpyAsync(dev[k] + lo, host[k] + 4 * lo, (hi - lo) * sizeof(fr_t), cudaMemcpyHostToDevice, st));
+        for (int r = 0; r < shard_world; r++) {
+            const size_t rlo = std::min(cn, (size_t)r * chunk), rhi = std::min(cn, rlo + chunk);
+            for (int k = 0; k < 5 && rhi > rlo; k++)
+                if (dev_bcast(dev_bcast_user, dev[k] + rlo, (rhi - rlo) * sizeof(fr_t), r) != 0)
+                    throw std::runtime_error("device broadcast of a witness slice failed");
+        }
+    } else {
+        for (int k = 0; k < 5; k++) ZP_CUDA(cudaMemcpyAsync(dev[k], host[k], cn * sizeof(fr_t), cudaMemcpyHostToDevice, st));
     }
-    ZP_CUDA(cudaMemcpyAsync(qlk_ev.p, c.q_lookup, cn * sizeof(fr_t), cudaMemcpyHostToDevice, st));
+    for (int k = 0; k < 4; k++)
+        if (cn < n) ZP_CUDA(cudaMemsetAsync(w_ev[k].p + cn, 0, (n - cn) * sizeof(fr_t), st));
     wit_lookup_on = !(table_zero && all_zero(PS, qlk_ev.p, cn, st));
     if (wit_lookup_on) ensure_work_buffers(true);
     wit_n = cn;
