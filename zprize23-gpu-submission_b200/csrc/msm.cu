@@ -1,13 +1,15 @@
 // Pippenger MSM over BLS12-381 G1 for sm_100a — see msm.cuh / DESIGN.md §MSM.
 //
-// Pipeline (all on one stream, no host round trip until the 16 window sums come back):
-//   1. digits    : Montgomery scalar -> canonical -> signed c-bit digits, per-(window,bucket) histogram
-//   2. scan      : exclusive scan of the histogram (bucket start offsets), one CTA
-//   3. scatter   : counting-sort the point indices into (window,bucket) runs (atomic cursor per bucket)
-//   4. accumulate: one thread per work segment (<= 2x mean bucket load) of a bucket, XYZZ mixed additions
-//                  (the IMAD-bound hot loop); long buckets are split so no digit distribution serialises
-//   5. reduce    : row / column sums of the bucket matrix, then weight * sum and a tree (msm_rowcol_kernel, msm_weighted_kernel)
-//   host         : fold 8 partials per window, Horner over windows (256 doublings), to affine
+// Pipeline of one batch of k <= 8 scalar vectors over the same points (all on one stream; host round trips: the root
+// inversion of each batch-affine round and the k final sums):
+//   1. digits    : Montgomery scalar -> canonical -> signed c-bit digits, per-(member, window / set, bucket) histogram
+//   2. scan      : exclusive scan of the histogram (bucket start offsets), multi-CTA
+//   3. scatter   : counting-sort the point indices into bucket runs (atomic cursor per bucket)
+//   4. rounds    : batch-affine pairwise additions inside every run (msm_affine.cuh), 4 rounds by default
+//   5. accumulate: what is left (1/16 of the entries): one thread per work segment, XYZZ mixed additions, persistent
+//                  threads; long buckets are split so no digit distribution serialises
+//   6. reduce    : row / column sums of the bucket matrix, then weight * sum and a tree (msm_rowcol_kernel, msm_weighted_kernel)
+//   host         : with precomputed window tables one XYZZ point per member; otherwise Horner over the window sums; to affine
 // Order inside a bucket is not deterministic (atomics) but the group sum is exact, so the affine
 // result is bit-identical run to run.
 #include "msm.cuh"

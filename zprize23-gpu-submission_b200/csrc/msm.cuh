@@ -47,7 +47,7 @@ struct MsmWorkspace {
     DevBuf<uint32_t> seg_start;// [nwin*nbuckets + 1] exclusive scan of ceil(bucket size / seg) (work segments)
     DevBuf<uint32_t> seg_cnt;  // [nwin*nbuckets]
     DevBuf<xyzz_t> segs;       // [<= nwin*n/seg + nwin*nbuckets] partial sum of each work segment
-    DevBuf<uint2> desc;        // [max_segs] (first, last+1) index into `sorted` of each work segment
+    DevBuf<uint2> desc;        // [<= nwin*n/seg + nwin*nbuckets] (first, last+1) index into `sorted` of each work segment
     DevBuf<uint32_t> counter;  // dynamic segment counter of the persistent accumulate kernel
     DevBuf<uint32_t> tile_sum; // scratch of the multi-CTA scan
     int sm_count = 0;
@@ -80,7 +80,6 @@ struct MsmWorkspace {
     double down0_ms = 0, down0_pairs = 0;
     int down0_launches = 0;
     size_t seg = 0;            // points per work segment (2x the mean bucket load, >= 32)
-    size_t max_segs = 0;
     DevBuf<xyzz_t> rowcol;     // [nsets][W1 + W2] row / column sums of the bucket matrix (bucket reduction, step 1)
     DevBuf<xyzz_t> partial;    // [nsets][groups] weighted partial sums (bucket reduction, step 2)
     DevBuf<xyzz_t> final_sums; // [nsets] per-set sums (what returns to the host)
