@@ -302,10 +302,11 @@ int zpo_combine_split(size_t n, const uint64_t* t, const uint64_t* f, uint64_t* 
 
 // ---- circuit / prover / verifier context --------------------------------------------------------
 // with_pk: 0 = circuit + selector evaluations only (pk built elsewhere), 1 = full CPU preprocessing
-void* zpo_ctx_new(int height, uint64_t witness_seed, uint64_t tau_seed, int n_lookup, int with_pk, int with_srs) {
+// kind: 0 Poseidon-Merkle tree of `height`; 1..3 the gadget circuits of build_custom_circuit (height ignored)
+void* zpo_ctx_new_kind(int kind, int height, uint64_t witness_seed, uint64_t tau_seed, int n_lookup, int with_pk, int with_srs) {
     ensure_init();
     OracleCtx* c = new OracleCtx();
-    c->cs = build_merkle_circuit(height, witness_seed, n_lookup);
+    c->cs = kind == 0 ? build_merkle_circuit(height, witness_seed, n_lookup) : build_custom_circuit(kind, witness_seed, n_lookup);
     size_t bound = std::max(c->cs.n(), c->cs.table.size());
     int logn = log2_ceil(bound);
     size_t N = (size_t)1 << logn;
@@ -346,10 +347,19 @@ void* zpo_ctx_new(int height, uint64_t witness_seed, uint64_t tau_seed, int n_lo
             memcpy(&c->srs_raw[12 * i + 6], c->srs[i].y.v, 48);
         }
     }
-    assert(c->cs.pi.size() == 1);
-    c->pi_pos = c->cs.pi[0].first;
-    c->cs.pi[0].second.to_canonical(c->pi_canonical);
+    // the FFI carries exactly one public input (CircuitC.pi / intended_pi_pos); a circuit without one passes pi = 0,
+    // which PublicInputs drops (pi.rs:55-62)
+    assert(c->cs.pi.size() <= 1);
+    c->pi_pos = 0;
+    memset(c->pi_canonical, 0, 32);
+    if (c->cs.pi.size() == 1) {
+        c->pi_pos = c->cs.pi[0].first;
+        c->cs.pi[0].second.to_canonical(c->pi_canonical);
+    }
     return c;
+}
+void* zpo_ctx_new(int height, uint64_t witness_seed, uint64_t tau_seed, int n_lookup, int with_pk, int with_srs) {
+    return zpo_ctx_new_kind(0, height, witness_seed, tau_seed, n_lookup, with_pk, with_srs);
 }
 void zpo_ctx_free(void* h) { delete (OracleCtx*)h; }
 uint64_t zpo_ctx_n(void* h) { return ((OracleCtx*)h)->cs.n(); }
@@ -368,21 +378,45 @@ const uint64_t* zpo_ctx_v_h_coset_8n(void* h) { return (const uint64_t*)((Oracle
 const uint64_t* zpo_ctx_srs(void* h) { return ((OracleCtx*)h)->srs_raw.data(); }
 const uint64_t* zpo_ctx_tau(void* h) { return ((OracleCtx*)h)->tau.v; }
 
-// every gate equation of the synthetic circuit holds on the witness (sanity of the generator itself)
+// every gate equation of the synthetic circuit holds on the witness (sanity of the generator itself): arithmetic + PI
+// + the four custom widgets (separation challenges drawn at random) on every row, "next" = the following row, and
+// every lookup row is in the table
 int zpo_ctx_check_satisfied(void* h) {
     OracleCtx* c = (OracleCtx*)h;
     Composer& cs = c->cs;
-    std::vector<Fr> pi(cs.n(), Fr::zero());
+    const size_t n = cs.n();
+    std::vector<Fr> pi(n, Fr::zero());
     for (auto& e : cs.pi) pi[e.first] = e.second;
-    for (size_t i = 0; i < cs.n(); i++) {
-        Fr a = c->w[0][i], b = c->w[1][i], o = c->w[2][i], d = c->w[3][i];
-        Fr v = (a * b * cs.q[Q_M][i] + a * cs.q[Q_L][i] + b * cs.q[Q_R][i] + o * cs.q[Q_O][i] + d * cs.q[Q_4][i] +
-                a.pow_u64(5) * cs.q[Q_HL][i] + b.pow_u64(5) * cs.q[Q_HR][i] + d.pow_u64(5) * cs.q[Q_H4][i] + cs.q[Q_C][i]) *
+    SplitMix64 rng(0x5e9a);
+    Fr rs = rng.next_fr(), ls = rng.next_fr(), fs = rng.next_fr(), vs = rng.next_fr();
+    auto wv = [&](int k, size_t i) { return i < n ? c->w[k][i] : Fr::zero(); };
+    for (size_t i = 0; i < n; i++) {
+        GateVals g;
+        g.a = wv(0, i); g.b = wv(1, i); g.c = wv(2, i); g.d = wv(3, i);
+        g.a_next = wv(0, i + 1); g.b_next = wv(1, i + 1); g.d_next = wv(3, i + 1);
+        g.q_l = cs.q[Q_L][i]; g.q_r = cs.q[Q_R][i]; g.q_c = cs.q[Q_C][i];
+        Fr v = (g.a * g.b * cs.q[Q_M][i] + g.a * cs.q[Q_L][i] + g.b * cs.q[Q_R][i] + g.c * cs.q[Q_O][i] + g.d * cs.q[Q_4][i] +
+                g.a.pow_u64(5) * cs.q[Q_HL][i] + g.b.pow_u64(5) * cs.q[Q_HR][i] + g.d.pow_u64(5) * cs.q[Q_H4][i] + cs.q[Q_C][i]) *
                    cs.q[Q_ARITH][i] +
                pi[i];
+        v = v + cs.q[Q_RANGE][i] * range_constraints(rs, g) + cs.q[Q_LOGIC][i] * logic_constraints(ls, g) +
+            cs.q[Q_FIXED][i] * fbsm_constraints(fs, g) + cs.q[Q_VAR][i] * curve_add_constraints(vs, g);
         if (!v.is_zero()) return 0;
+        if (!cs.q[Q_LOOKUP][i].is_zero()) {
+            bool found = false;
+            for (auto& row : cs.table)
+                if (row[0] == g.a && row[1] == g.b && row[2] == g.c && row[3] == g.d) found = true;
+            if (!found) return 0;
+        }
     }
+    // copy constraints: every cell of a variable's cycle holds the variable's value
+    for (auto& e : cs.perm_log)
+        if (!(c->w[e.second & 3][e.second >> 2] == cs.var_vals[e.first])) return 0;
     return 1;
+}
+int zpo_te_generator_on_curve() {
+    ensure_init();
+    return te_on_curve(te_generator()) && (-jubjub_d() == Fr::from_u64(10240) * Fr::from_u64(10241).inverse()) ? 1 : 0;
 }
 
 // Runs the CPU restatement of the prover; proof_out = 2656-byte ProofC image; returns seconds.

@@ -28,6 +28,8 @@ class Oracle:
         vp, ci, cs, c64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_uint64
         L.zpo_ctx_new.restype = vp
         L.zpo_ctx_new.argtypes = [ci, c64, c64, ci, ci, ci]
+        L.zpo_ctx_new_kind.restype = vp
+        L.zpo_ctx_new_kind.argtypes = [ci, ci, c64, c64, ci, ci, ci]
         L.zpo_ctx_free.argtypes = [vp]
         for name in ["zpo_ctx_n", "zpo_ctx_lookup_len", "zpo_ctx_pi_pos"]:
             getattr(L, name).restype = c64
@@ -141,10 +143,12 @@ def encode_script(ops):
 class OracleCircuit:
     """A synthetic Merkle-tree circuit + prover key + SRS held by the oracle, exposed as numpy views."""
 
-    def __init__(self, oracle, height, witness_seed=42, tau_seed=7, n_lookup=0, with_pk=True, with_srs=True):
+    # kind: 0 Poseidon-Merkle tree of `height`; 1 all TurboPLONK widgets (range, logic, fixed-base, curve addition, q_m,
+    # Poseidon rounds, optional lookups); 2 no constants (q_c == 0); 3 no arithmetic gates (q_arith == 0, no public input)
+    def __init__(self, oracle, height, witness_seed=42, tau_seed=7, n_lookup=0, with_pk=True, with_srs=True, kind=0):
         self.o = oracle
         L = oracle.lib
-        self.h = L.zpo_ctx_new(height, witness_seed, tau_seed, n_lookup, 1 if with_pk else 0, 1 if with_srs else 0)
+        self.h = L.zpo_ctx_new_kind(kind, height, witness_seed, tau_seed, n_lookup, 1 if with_pk else 0, 1 if with_srs else 0)
         self.cs_n = L.zpo_ctx_n(self.h)
         self.log_n = L.zpo_ctx_logn(self.h)
         self.n = 1 << self.log_n

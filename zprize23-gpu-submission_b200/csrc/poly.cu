@@ -505,7 +505,7 @@ __global__ void __launch_bounds__(128) quotient_kernel(QuotientArgs a) {
     g.d = load_fr(&a.w[3][wi]);
 
     // ---- arithmetic widget (arithmetic.rs:61-79)
-    fr_t arith = load_fr(&a.sel[5][i]);  // q_c
+    fr_t arith = a.sel[5] ? load_fr(&a.sel[5][i]) : fr_t::zero();  // q_c (dropped when identically zero, like every selector)
     g.q_c = arith;
     if (a.sel[0]) arith = arith + g.a * g.b * load_fr(&a.sel[0][i]);
     g.q_l = a.sel[1] ? load_fr(&a.sel[1][i]) : fr_t::zero();
