@@ -99,10 +99,15 @@ typedef struct {
 } CommitKeyC;
 
 /* ---- the drop-in symbol (lib.rs:237-239) ------------------------------------------------------
- * Uploads the prover key and SRS on the first call for a given (pk, ck) pointer set and keeps them
- * resident in HBM for later calls (disable with ZPRIZE_B200_PK_CACHE=0).
- * Like the reference it has no error channel: a CUDA failure prints a message and exits(1). */
+ * Uploads the prover key and SRS on the first call and keeps them resident in HBM for later calls with the SAME KEY
+ * CONTENT (domain size + fingerprint of every pk array, the tables and the SRS; addresses are irrelevant, so the
+ * reference's `pk.clone()`-per-proof pattern, benches/pnp_bench.rs:70, hits the cache).  ZPRIZE_B200_PK_CACHE = "0"
+ * disables caching, "full" fingerprints every word instead of a strided sample; see INTEGRATION.md.
+ * Like the reference it has no error channel: a failure (CUDA error, domain outside [2^6, 2^23], public-input position
+ * outside the domain) prints a message and exits(1) (lib/caffe/common.hpp:23-30). */
 ProofC gen_proof(CircuitC circuit, ProverKeyC pk, CommitKeyC ck);
+/* Drops the context gen_proof keeps resident (frees its HBM); the next call uploads again. */
+void zp_gen_proof_invalidate(void);
 
 /* ---- resident prover context (extension) ------------------------------------------------------ */
 typedef struct zp_prover zp_prover;
@@ -142,6 +147,10 @@ int zp_prover_load_pk(zp_prover* p, const ProverKeyC* pk, const uint64_t* coeff_
  * columns followed by the 4 sigma columns as evaluations on H (N Fr each, host memory, NULL = all
  * zero); tables[4] the padded lookup columns (N Fr each, NULL = all zero). */
 int zp_prover_preprocess(zp_prover* p, const uint64_t* const* selector_evals, const uint64_t* const* tables);
+/* Copy one prover-key polynomial back in the FFI layout: index 0..18 in ProverKeyC order (coeffs_out: N Fr, evals_out:
+ * 8N Fr, either may be NULL), index 19..22 = lookup table columns (N Fr through coeffs_out).  With zp_prover_preprocess
+ * this is the device twin of `preprocess_prover` (preprocess.rs:162-295) producing the ProverKeyC arrays. */
+int zp_prover_read_pk(zp_prover* p, int index, uint64_t* coeffs_out, uint64_t* evals_out);
 /* Commitments to the 19 prover-key polynomials + 4 table polynomials (verifier key), 23 * 12 u64. */
 int zp_prover_verifier_key(zp_prover* p, uint64_t* out_commitments);
 /* One proof with the resident key.  Host pointers in `circuit`; returns 0 on success. */
@@ -212,6 +221,13 @@ int zp_poly_divide_host(zp_prover* p, const uint64_t* coeffs, size_t n, const ui
 /* plookup MultiSet::combine_split(t, f) (lookup/multiset.rs:131-176) on the device: n-element host arrays t, f in,
  * h1, h2 out.  Returns 0, or -1 with "ElementNotIndexed" when an element of f is missing from t. */
 int zp_combine_split_host(zp_prover* p, const uint64_t* t, const uint64_t* f, size_t n, uint64_t* h1, uint64_t* h2);
+/* The same for multisets of different cardinality (the shape of the reference's own known-answer test,
+ * lookup/multiset.rs:335-393): h1 receives ceil((nt + nf) / 2) elements, h2 floor((nt + nf) / 2). */
+int zp_multiset_combine_split_host(zp_prover* p, const uint64_t* t, size_t nt, const uint64_t* f, size_t nf, uint64_t* h1,
+                                   uint64_t* h2);
+/* MultiSet::compress of four columns (lookup/multiset.rs:207-213; `lc`, util.rs:154-176):
+ * out[i] = c0[i] + ch c1[i] + ch^2 c2[i] + ch^3 c3[i]; columns = 4 host arrays of n Fr. */
+int zp_multiset_compress_host(zp_prover* p, const uint64_t* const* columns, size_t n, const uint64_t* challenge, uint64_t* out);
 /* exclusive prefix product (the z(X) scan primitive) */
 int zp_prefix_product_host(zp_prover* p, const uint64_t* in, size_t n, uint64_t* out);
 
@@ -221,6 +237,9 @@ int zp_bench_upload(zp_prover* p, int slot, const uint64_t* host, size_t n_fr);
 int zp_bench_download(zp_prover* p, int slot, uint64_t* host, size_t n_fr);
 /* runs `iters` transforms slot_in -> slot_out on the stream; returns average device ms via *ms */
 int zp_bench_ntt(zp_prover* p, int kind, int log_n, int slot_in, int slot_out, int iters, double* ms);
+/* the same for n_in coefficients implicitly zero-padded to 2^log_n (kind 2 with log_n = logN + 3, n_in = N is the
+ * extended-coset transform of the quotient round; reference: Ntt_coset::forward, function.cu:261-268) */
+int zp_bench_ntt_padded(zp_prover* p, int kind, int log_n, size_t n_in, int slot_in, int slot_out, int iters, double* ms);
 /* runs `iters` MSMs of n points with scalars in `slot`; *ms = average device ms (host tail included) */
 int zp_bench_msm(zp_prover* p, int slot, size_t n, int iters, double* ms, uint64_t* out_affine);
 /* the same for `nbatch` (<= 8) scalar vectors over the same points in ONE pipeline (the batch the prover uses for

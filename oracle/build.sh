@@ -11,7 +11,7 @@ cd "$(dirname "$0")"
 CXX=${ZP_CXX:-g++}
 CC=${ZP_CC:-gcc}
 if [ ! -f liboracle.so ] || [ -n "$(find . -maxdepth 1 \( -name '*.hpp' -o -name '*.cpp' \) -newer liboracle.so)" ]; then
-  $CXX -std=c++17 -O2 -fopenmp -fPIC -shared -Wall -Wno-unused-function -o liboracle.so oracle_capi.cpp
+  $CXX -std=c++17 -O2 -fopenmp -fPIC -shared -Wall -Wno-unused-function -o liboracle.so oracle_capi.cpp -ldl
 fi
 REF="${ZP_REFERENCE_ROOT:-/root/reference}/Prize 1B/plonk-core/lib"
 if [ -d "$REF" ]; then

@@ -12,8 +12,16 @@ REF="${ZP_REFERENCE_ROOT:-/root/reference}/Prize 1B/plonk-core/lib"
 [ -d "$REF" ] || { echo "reference not present; skipping"; exit 0; }
 mkdir -p _ref/pnp_obj
 OUT=_ref/libzprize_ref.so
-[ -f "$OUT" ] && { echo "$OUT exists"; exit 0; }
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+# extern "C" driver over the reference's operator API (ref_ops.cu), linked against the library above
+build_ops() {
+  if [ ! -f _ref/libref_ops.so ] || [ ref_ops.cu -nt _ref/libref_ops.so ]; then
+    "$NVCC" -std=c++17 -O3 -arch=sm_100 -Xcompiler -fPIC -ccbin g++ -w -include cstdint -I"$REF" -I"$REF/blst/include" \
+        -shared ref_ops.cu -o _ref/libref_ops.so -L_ref -lzprize_ref -Xlinker -rpath -Xlinker '$ORIGIN' -lcudart
+    echo "built _ref/libref_ops.so"
+  fi
+}
+[ -f "$OUT" ] && { echo "$OUT exists"; build_ops; exit 0; }
 gcc -O2 -mno-avx -fno-builtin -Wno-unused-function -fPIC -D__BLST_PORTABLE__ -I"$REF/blst/include" \
     -c "$REF/blst/src/server.c" -o _ref/pnp_obj/blst_server.o
 gcc -O2 -fPIC -c "$REF/blst/src/assembly.S" -o _ref/pnp_obj/blst_asm.o
@@ -30,3 +38,4 @@ wait || true
 "$NVCC" -shared -arch=sm_100 -o "$OUT" _ref/pnp_obj/*.o -lcudart -lpthread
 rm -rf _ref/pnp_obj
 echo "built $OUT"
+build_ops

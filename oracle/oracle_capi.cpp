@@ -58,6 +58,24 @@ int zpo_num_threads() {
 #endif
 }
 
+// blst acceleration of the CPU baseline (zp_field.hpp): returns 1 when active after the call
+int zpo_set_blst(int on) {
+    ensure_init();
+    blst_api().on = on && blst_api().loaded;
+    return blst_api().on ? 1 : 0;
+}
+int zpo_blst_active() {
+    ensure_init();
+    return blst_api().on ? 1 : 0;
+}
+void zpo_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 // ---- constants (for pinning against the reference's literals) -------------------------------
 void zpo_fr_constants(uint64_t* modulus, uint64_t* one, uint64_t* rr, uint64_t* inv, uint64_t* two_adic_root,
                       uint64_t* generator) {
@@ -286,6 +304,56 @@ size_t zpo_proof_serialize(const uint64_t* proof_in, uint8_t* out) {
         o += 32;
     }
     return (size_t)(o - out);
+}
+
+// ---- sigma permutations from a wire map (permutation/mod.rs:101-166): vars = 4 columns (left, right, output, fourth)
+// of n_gates variable ids added gate by gate with add_variables_to_map.  code[k * N + i] = (wire << 28) | gate of
+// sigma_k(i) (WireData), enc = its field encoding K_wire * omega^gate (compute_permutation_lagrange), N = 2^logn.
+void zpo_sigma_from_wires(int logn, size_t n_gates, const uint32_t* vars, size_t n_vars, uint32_t* code, uint64_t* enc) {
+    ensure_init();
+    Composer cs;
+    for (size_t v = 0; v < n_vars; v++) cs.add_input(Fr::zero());
+    for (size_t g = 0; g < n_gates; g++) cs.push_gate(vars[g], vars[n_gates + g], vars[2 * n_gates + g], vars[3 * n_gates + g]);
+    Domain dom(logn);
+    std::vector<Fr> sigma[4];
+    compute_sigma_evals(cs, dom, sigma);
+    for (int k = 0; k < 4; k++)
+        for (size_t i = 0; i < dom.n; i++) {
+            memcpy(enc + 4 * (k * dom.n + i), sigma[k][i].v, 32);
+            // decode: which (wire, gate) has this encoding
+            uint32_t c = 0xffffffffu;
+            for (int w = 0; w < 4 && c == 0xffffffffu; w++)
+                for (size_t j = 0; j < dom.n; j++)
+                    if (K_const(w) * dom.element(j) == sigma[k][i]) {
+                        c = ((uint32_t)w << 28) | (uint32_t)j;
+                        break;
+                    }
+            code[k * dom.n + i] = c;
+        }
+}
+// util.rs:154-176 lc(values, challenge) for k scalars
+void zpo_lc(size_t k, const uint64_t* values, const uint64_t* challenge, uint64_t* out) {
+    ensure_init();
+    Fr ch, acc;
+    memcpy(ch.v, challenge, 32);
+    memcpy(acc.v, values + 4 * (k - 1), 32);
+    for (size_t i = k - 1; i-- > 0;) {
+        Fr v;
+        memcpy(v.v, values + 4 * i, 32);
+        acc = acc * ch + v;
+    }
+    memcpy(out, acc.v, 32);
+}
+// combine_split for multisets of different cardinality; returns 0 on ElementNotIndexed
+int zpo_multiset_combine_split(size_t nt, const uint64_t* t, size_t nf, const uint64_t* f, uint64_t* h1, uint64_t* h2) {
+    ensure_init();
+    std::vector<Fr> tv(nt), fv(nf), a, b;
+    memcpy(tv.data(), t, 32 * nt);
+    if (nf) memcpy(fv.data(), f, 32 * nf);
+    if (!combine_split(tv, fv, a, b)) return 0;
+    memcpy(h1, a.data(), 32 * a.size());
+    if (!b.empty()) memcpy(h2, b.data(), 32 * b.size());
+    return 1;
 }
 
 // ---- combine_split (multiset.rs:131-176) ------------------------------------------------------

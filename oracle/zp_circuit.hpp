@@ -609,6 +609,13 @@ static inline ProverKeyO preprocess(const Composer& cs) {
     for (int s = 0; s < NUM_PK_POLYS; s++) {
         std::vector<Fr> ev = s < NUM_SELECTORS ? cs.q[s] : sigma[s - NUM_SELECTORS];
         ev.resize(pk.n, Fr::zero());
+        bool all_zero = true;
+        for (size_t i = 0; i < ev.size() && all_zero; i++) all_zero = ev[i].is_zero();
+        if (all_zero) {  // the transform of the zero vector, without running it
+            pk.coeffs[s].assign(pk.n, Fr::zero());
+            pk.evals[s].assign(8 * pk.n, Fr::zero());
+            continue;
+        }
         pk.coeffs[s] = dom.ifft(ev);
         pk.evals[s] = dom8.coset_fft(pk.coeffs[s]);
     }
@@ -618,8 +625,13 @@ static inline ProverKeyO preprocess(const Composer& cs) {
         if (t.empty()) t.push_back(Fr::zero());
         t.resize(pk.n, t[0]);  // multiset.rs:70-79
     }
-    std::vector<Fr> x = {Fr::zero(), Fr::one()};
-    pk.linear_evaluations = dom8.coset_fft(x);
+    // coset_fft of the polynomial X: the coset points g * omega_8N^i themselves (preprocess.rs:281-284)
+    pk.linear_evaluations.resize(8 * pk.n);
+    {
+        const Fr g = fr_generator();
+#pragma omp parallel for schedule(static)
+        for (long i = 0; i < (long)(8 * pk.n); i++) pk.linear_evaluations[i] = g * dom8.element(i);
+    }
     // preprocess.rs:498-520
     pk.v_h_coset_8n.resize(8 * pk.n);
     Fr cg = fr_generator().pow_u64(pk.n);

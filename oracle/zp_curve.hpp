@@ -8,6 +8,9 @@
 // Only the affine result of any group computation is observable, so any exact algorithm is bit-exact.
 #pragma once
 #include "zp_field.hpp"
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 namespace zpo {
 
@@ -150,10 +153,46 @@ static inline void g1_batch_to_affine(const std::vector<G1>& in, std::vector<G1A
     }
 }
 
+static inline bool g1_msm_uses_blst() { return blst_api().on; }
+
 // Bucket-method MSM over canonical scalars (window c, unsigned digits), OpenMP over windows.
 // Restates `VariableBaseMSM::multi_scalar_mul` (ark-ec 0.3.0): exact group sum.
 static inline G1 g1_msm(const G1Affine* pts, const Fr* scalars, size_t n) {
     if (n == 0) return G1::infinity();
+    if (blst_api().on && n >= 32) {
+        // point-range slices, one blst Pippenger per host thread, partial sums added in slice order
+        int threads = 1;
+#ifdef _OPENMP
+        threads = omp_get_max_threads();
+#endif
+        size_t per = (n + threads - 1) / threads;
+        if (per < 16) per = 16;
+        int slices = (int)((n + per - 1) / per);
+        std::vector<G1> part(slices, G1::infinity());
+        bool any_inf = false;
+        for (size_t i = 0; i < n && !any_inf; i++) any_inf = pts[i].inf;
+        if (!any_inf) {
+#pragma omp parallel for schedule(static, 1)
+            for (int t = 0; t < slices; t++) {
+                size_t lo = (size_t)t * per, hi = std::min(n, lo + per), m = hi - lo;
+                std::vector<uint64_t> xy(12 * m), sc(4 * m);
+                for (size_t i = 0; i < m; i++) {
+                    memcpy(&xy[12 * i], pts[lo + i].x.v, 48);
+                    memcpy(&xy[12 * i + 6], pts[lo + i].y.v, 48);
+                    scalars[lo + i].to_canonical(&sc[4 * i]);
+                }
+                std::vector<uint64_t> scratch(blst_api().scratch_sizeof(m) / 8 + 1);
+                const void* pp[2] = {xy.data(), nullptr};
+                const void* sp[2] = {sc.data(), nullptr};
+                G1 r;
+                blst_api().pippenger(&r, pp, m, sp, 255, scratch.data());
+                part[t] = r;
+            }
+            G1 total = G1::infinity();
+            for (int t = 0; t < slices; t++) total = total.add(part[t]);
+            return total;
+        }
+    }
     int c = 3;
     while ((1ull << (c + 1)) * 4 < n && c < 15) c++;
     int nwin = (255 + c - 1) / c;

@@ -16,6 +16,8 @@
 #include <cassert>
 #include <string>
 #include <vector>
+#include <dlfcn.h>
+#include <cstdlib>
 
 namespace zpo {
 
@@ -84,6 +86,44 @@ struct FieldParams {
     }
 };
 
+// ---- optional accelerator for the CPU baseline: the reference's OWN vendored blst ("Prize 1B/plonk-core/lib/blst",
+// compiled where it lies into oracle/_ref/libref_blst.so by build.sh).  `blst_fr_mul` / `blst_fp_mul` are the asm
+// Montgomery products and `blst_p1s_mult_pippenger` the CPU MSM the reference links (build.rs:54,61).  Loaded at run
+// time from next to liboracle.so; ZPO_NO_BLST=1 or zpo_set_blst(0) selects the plain C++ arithmetic so that the tests
+// can compare the two.  All results are canonical field elements / exact group sums, hence byte-identical either way.
+struct BlstApi {
+    void (*fr_mul)(uint64_t* r, const uint64_t* a, const uint64_t* b) = nullptr;
+    void (*fp_mul)(uint64_t* r, const uint64_t* a, const uint64_t* b) = nullptr;
+    size_t (*scratch_sizeof)(size_t) = nullptr;
+    void (*pippenger)(void* ret, const void* const points[], size_t npoints, const void* const scalars[], size_t nbits,
+                      void* scratch) = nullptr;
+    void* handle = nullptr;
+    bool loaded = false;  // library found with every symbol
+    bool on = false;      // currently used
+};
+static inline BlstApi& blst_api() {
+    static BlstApi api;
+    return api;
+}
+static inline void blst_load(const void* addr_in_this_library) {
+    BlstApi& a = blst_api();
+    if (a.handle) return;
+    Dl_info info;
+    if (!dladdr(addr_in_this_library, &info) || !info.dli_fname) return;
+    std::string path(info.dli_fname);
+    size_t slash = path.rfind('/');
+    path = (slash == std::string::npos ? std::string(".") : path.substr(0, slash)) + "/_ref/libref_blst.so";
+    a.handle = dlopen(path.c_str(), RTLD_NOW | RTLD_LOCAL);
+    if (!a.handle) return;
+    a.fr_mul = (void (*)(uint64_t*, const uint64_t*, const uint64_t*))dlsym(a.handle, "blst_fr_mul");
+    a.fp_mul = (void (*)(uint64_t*, const uint64_t*, const uint64_t*))dlsym(a.handle, "blst_fp_mul");
+    a.scratch_sizeof = (size_t(*)(size_t))dlsym(a.handle, "blst_p1s_mult_pippenger_scratch_sizeof");
+    a.pippenger = (void (*)(void*, const void* const[], size_t, const void* const[], size_t, void*))dlsym(a.handle, "blst_p1s_mult_pippenger");
+    a.loaded = a.fr_mul && a.fp_mul && a.scratch_sizeof && a.pippenger;
+    const char* off = getenv("ZPO_NO_BLST");
+    a.on = a.loaded && !(off && off[0] == '1');
+}
+
 template <int N, int TAG>
 struct Fp {
     uint64_t v[N];
@@ -130,6 +170,14 @@ struct Fp {
     }
     // CIOS Montgomery product; result canonical.
     Fp operator*(const Fp& o) const {
+        if (blst_api().on) {
+            Fp r;
+            if (N == 4)
+                blst_api().fr_mul(r.v, v, o.v);
+            else
+                blst_api().fp_mul(r.v, v, o.v);
+            return r;
+        }
         const uint64_t* p = P().p;
         const uint64_t inv = P().inv;
         uint64_t t[N + 2];
@@ -251,6 +299,7 @@ struct FieldInit {
     FieldInit() {
         Fr::P().init(FR_MODULUS, 255);
         Fq::P().init(FQ_MODULUS, 381);
+        blst_load((const void*)FR_MODULUS);
     }
 };
 static inline void ensure_init() { static FieldInit once; (void)once; }

@@ -59,12 +59,31 @@ struct Domain {
     void transform(std::vector<Fr>& a, const std::vector<Fr>& t) const {
         assert(a.size() == n);
         // bit reversal
-        for (size_t i = 0; i < n; i++) {
+#pragma omp parallel for schedule(static) if (n >= 4096)
+        for (long ii = 0; ii < (long)n; ii++) {
+            size_t i = (size_t)ii;
             size_t j = 0;
             for (int b = 0; b < logn; b++) j |= ((i >> b) & 1) << (logn - 1 - b);
             if (i < j) std::swap(a[i], a[j]);
         }
-        for (int s = 1; s <= logn; s++) {
+        // the first LB stages touch blocks of 2^LB consecutive elements only: run them block by block (cache resident,
+        // one thread per block), the remaining stages sweep the whole array
+        const int LB = std::min(logn, 13);
+        const size_t BS = (size_t)1 << LB;
+#pragma omp parallel for schedule(static) if (n >= 4096)
+        for (long blk0 = 0; blk0 < (long)(n / BS); blk0++) {
+            Fr* x = a.data() + (size_t)blk0 * BS;
+            for (int s = 1; s <= LB; s++) {
+                size_t m = (size_t)1 << s, half = m >> 1, stride = n / m;
+                for (size_t b = 0; b < BS; b += m)
+                    for (size_t j = 0; j < half; j++) {
+                        Fr u = x[b + j], v = x[b + j + half] * t[j * stride];
+                        x[b + j] = u + v;
+                        x[b + j + half] = u - v;
+                    }
+            }
+        }
+        for (int s = LB + 1; s <= logn; s++) {
             size_t m = (size_t)1 << s, half = m >> 1, stride = n / m;
 #pragma omp parallel for schedule(static) if (n >= 4096)
             for (long k = 0; k < (long)(n / 2); k++) {

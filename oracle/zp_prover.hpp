@@ -25,6 +25,7 @@
 #include <unordered_map>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 
 namespace zpo {
 
@@ -50,20 +51,33 @@ struct Challenges {
 // JubJub (ed-on-bls12-381) parameters for the ECC gates: a = -1, d = -(10240/10241)
 // (in-tree Montgomery literals: "…/lib/PLONK/src/bls12_381/edwards.cu":5-31).
 static inline Fr jubjub_a() { return -Fr::one(); }
-static inline Fr jubjub_d() { return -(Fr::from_u64(10240) * Fr::from_u64(10241).inverse()); }
+static inline const Fr& jubjub_d() {
+    static const Fr d = -(Fr::from_u64(10240) * Fr::from_u64(10241).inverse());
+    return d;
+}
+// Montgomery forms of the small integers the widgets use, converted once
+static inline const Fr& small_fr(unsigned k) {
+    static const std::vector<Fr> tab = [] {
+        ensure_init();
+        std::vector<Fr> t(128);
+        for (unsigned i = 0; i < 128; i++) t[i] = Fr::from_u64(i);
+        return t;
+    }();
+    return tab[k];
+}
 
 static inline Fr lc4(const Fr& a, const Fr& b, const Fr& c, const Fr& d, const Fr& ch) {
     return ((d * ch + c) * ch + b) * ch + a;  // util.rs:170-175
 }
 static inline Fr delta4(const Fr& f) {  // f(f-1)(f-2)(f-3)
-    return f * (f - Fr::one()) * (f - Fr::from_u64(2)) * (f - Fr::from_u64(3));
+    return f * (f - small_fr(1)) * (f - small_fr(2)) * (f - small_fr(3));
 }
 
 struct GateVals {
     Fr a, b, c, d, a_next, b_next, d_next, q_l, q_r, q_c;
 };
 static inline Fr range_constraints(const Fr& sep, const GateVals& g) {  // range.rs:49-63
-    Fr four = Fr::from_u64(4);
+    const Fr& four = small_fr(4);
     Fr kappa = sep.square(), kappa_sq = kappa.square(), kappa_cu = kappa_sq * kappa;
     Fr b1 = delta4(g.c - four * g.d);
     Fr b2 = delta4(g.b - four * g.c) * kappa;
@@ -72,8 +86,8 @@ static inline Fr range_constraints(const Fr& sep, const GateVals& g) {  // range
     return (b1 + b2 + b3 + b4) * sep;
 }
 static inline Fr delta_xor_and(const Fr& a, const Fr& b, const Fr& w, const Fr& c, const Fr& q_c) {  // logic.rs:113-133
-    Fr nine = Fr::from_u64(9), two = Fr::from_u64(2), three = Fr::from_u64(3), four = Fr::from_u64(4);
-    Fr eighteen = Fr::from_u64(18), eighty_one = Fr::from_u64(81), eighty_three = Fr::from_u64(83);
+    const Fr &nine = small_fr(9), &two = small_fr(2), &three = small_fr(3), &four = small_fr(4);
+    const Fr &eighteen = small_fr(18), &eighty_one = small_fr(81), &eighty_three = small_fr(83);
     Fr F = w * (w * (four * w - eighteen * (a + b) + eighty_one) + eighteen * (a.square() + b.square()) -
                 eighty_one * (a + b) + eighty_three);
     Fr E = three * (a + b + c) - (two * F);
@@ -81,7 +95,7 @@ static inline Fr delta_xor_and(const Fr& a, const Fr& b, const Fr& w, const Fr& 
     return B + E;
 }
 static inline Fr logic_constraints(const Fr& sep, const GateVals& g) {  // logic.rs:66-91
-    Fr four = Fr::from_u64(4);
+    const Fr& four = small_fr(4);
     Fr kappa = sep.square(), kappa_sq = kappa.square(), kappa_cu = kappa_sq * kappa, kappa_qu = kappa_cu * kappa;
     Fr a = g.a_next - four * g.a;
     Fr c0 = delta4(a);
@@ -201,8 +215,20 @@ static inline G1Affine kzg_open(const std::vector<G1Affine>& srs, const std::vec
     return kzg_commit(srs, w);
 }
 
+struct PhaseClock {  // ZPO_DEBUG=1: wall time per protocol phase on stderr
+    bool on = getenv("ZPO_DEBUG") != nullptr;
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void lap(const char* what) {
+        if (!on) return;
+        auto n = std::chrono::steady_clock::now();
+        fprintf(stderr, "[zpo] %-28s %8.3f s\n", what, std::chrono::duration<double>(n - t).count());
+        t = n;
+    }
+};
+
 static inline ProofO prove(const ProverInput& in, Challenges* ch_out = nullptr) {
     ensure_init();
+    PhaseClock clk;
     const ProverKeyO& pk = *in.pk;
     const std::vector<G1Affine>& srs = *in.srs;
     const size_t n = pk.n, n8 = 8 * n;
@@ -225,6 +251,7 @@ static inline ProofO prove(const ProverInput& in, Challenges* ch_out = nullptr) 
     tr.append_g1("w_o", proof.comm[C_C]);
     tr.append_g1("w_4", proof.comm[C_D]);
 
+    clk.lap("1 wires: 4 ifft + 4 commit");
     // 2. lookup polynomials
     ch.zeta = tr.challenge_scalar("zeta");
     tr.append_fr("zeta", ch.zeta);
@@ -251,6 +278,7 @@ static inline ProofO prove(const ProverInput& in, Challenges* ch_out = nullptr) 
     tr.append_g1("h1", proof.comm[C_H1]);
     tr.append_g1("h2", proof.comm[C_H2]);
 
+    clk.lap("2 lookup polys");
     // 3. permutation polynomials
     ch.beta = tr.challenge_scalar("beta");
     tr.append_fr("beta", ch.beta);
@@ -310,6 +338,7 @@ static inline ProofO prove(const ProverInput& in, Challenges* ch_out = nullptr) 
     }
     proof.comm[C_Z2] = kzg_commit(srs, z2_poly);  // NOT appended to the transcript (prover.rs:395-397)
 
+    clk.lap("3 z, z2");
     std::vector<Fr> pi_ev(n, Fr::zero());
     for (auto& e : in.pi) pi_ev[e.first] = e.second;
     std::vector<Fr> pi_poly = dom.ifft(pi_ev);
@@ -343,6 +372,7 @@ static inline ProofO prove(const ProverInput& in, Challenges* ch_out = nullptr) 
         std::vector<Fr> f8 = dom8.coset_fft(f_poly), tb8 = dom8.coset_fft(table_poly);
         std::vector<Fr> h18 = dom8.coset_fft(h1_poly), h28 = dom8.coset_fft(h2_poly);
         std::vector<Fr> pi8 = dom8.coset_fft(pi_poly);
+        clk.lap("4a coset ffts");
         std::vector<Fr> quot(n8);
         Fr lsep_sq = ch.lookup_sep.square(), lsep_cu = lsep_sq * ch.lookup_sep;
         Fr opd = ch.delta + Fr::one(), eopd = ch.epsilon * opd;
@@ -391,7 +421,9 @@ static inline ProofO prove(const ProverInput& in, Challenges* ch_out = nullptr) 
             Fr lookup = la + lb + lcx + ld;
             quot[i] = (gate + perm + lookup) * vh_inv[i & 7];
         }
+        clk.lap("4b quotient pass");
         t_poly = dom8.coset_ifft(quot);
+        clk.lap("4c coset ifft");
         if (getenv("ZPO_DEBUG")) {
             size_t deg = 0;
             for (size_t i = 0; i < n8; i++)
@@ -407,38 +439,26 @@ static inline ProofO prove(const ProverInput& in, Challenges* ch_out = nullptr) 
     static const char* tl[8] = {"t_1", "t_2", "t_3", "t_4", "t_5", "t_6", "t_7", "t_8"};
     for (int k = 0; k < 8; k++) tr.append_g1(tl[k], proof.comm[C_T1 + k]);
 
+    clk.lap("4d t commits");
     // 5. linearisation
     ch.z = tr.challenge_scalar("z");
     tr.append_fr("z", ch.z);
     Fr zs = ch.z * dom.omega;
     Fr* e = proof.eval;
-    e[E_A] = poly_eval(w_poly[0], ch.z);
-    e[E_B] = poly_eval(w_poly[1], ch.z);
-    e[E_C] = poly_eval(w_poly[2], ch.z);
-    e[E_D] = poly_eval(w_poly[3], ch.z);
-    e[E_LSIG] = poly_eval(pk.coeffs[SIG_L], ch.z);
-    e[E_RSIG] = poly_eval(pk.coeffs[SIG_R], ch.z);
-    e[E_OSIG] = poly_eval(pk.coeffs[SIG_O], ch.z);
-    e[E_PERM] = poly_eval(z_poly, zs);
-    e[E_QARITH] = poly_eval(pk.coeffs[Q_ARITH], ch.z);
-    e[E_QLOOKUP] = poly_eval(pk.coeffs[Q_LOOKUP], ch.z);
-    e[E_QC] = poly_eval(pk.coeffs[Q_C], ch.z);
-    e[E_QL] = poly_eval(pk.coeffs[Q_L], ch.z);
-    e[E_QR] = poly_eval(pk.coeffs[Q_R], ch.z);
-    e[E_ANEXT] = poly_eval(w_poly[0], zs);
-    e[E_BNEXT] = poly_eval(w_poly[1], zs);
-    e[E_DNEXT] = poly_eval(w_poly[3], zs);
-    e[E_QHL] = poly_eval(pk.coeffs[Q_HL], ch.z);
-    e[E_QHR] = poly_eval(pk.coeffs[Q_HR], ch.z);
-    e[E_QH4] = poly_eval(pk.coeffs[Q_H4], ch.z);
-    e[E_Z2NEXT] = poly_eval(z2_poly, zs);
-    e[E_H1] = poly_eval(h1_poly, ch.z);
-    e[E_H1NEXT] = poly_eval(h1_poly, zs);
-    e[E_H2] = poly_eval(h2_poly, ch.z);
-    e[E_F] = poly_eval(f_poly, ch.z);
-    e[E_TABLE] = poly_eval(table_poly, ch.z);
-    e[E_TABLENEXT] = poly_eval(table_poly, zs);
-
+    {
+        struct EvalJob { int slot; const std::vector<Fr>* poly; bool shifted; };
+        const EvalJob jobs[NUM_EVAL] = {
+            {E_A, &w_poly[0], false}, {E_B, &w_poly[1], false}, {E_C, &w_poly[2], false}, {E_D, &w_poly[3], false},
+            {E_LSIG, &pk.coeffs[SIG_L], false}, {E_RSIG, &pk.coeffs[SIG_R], false}, {E_OSIG, &pk.coeffs[SIG_O], false},
+            {E_PERM, &z_poly, true}, {E_QARITH, &pk.coeffs[Q_ARITH], false}, {E_QLOOKUP, &pk.coeffs[Q_LOOKUP], false},
+            {E_QC, &pk.coeffs[Q_C], false}, {E_QL, &pk.coeffs[Q_L], false}, {E_QR, &pk.coeffs[Q_R], false},
+            {E_ANEXT, &w_poly[0], true}, {E_BNEXT, &w_poly[1], true}, {E_DNEXT, &w_poly[3], true},
+            {E_QHL, &pk.coeffs[Q_HL], false}, {E_QHR, &pk.coeffs[Q_HR], false}, {E_QH4, &pk.coeffs[Q_H4], false},
+            {E_Z2NEXT, &z2_poly, true}, {E_H1, &h1_poly, false}, {E_H1NEXT, &h1_poly, true}, {E_H2, &h2_poly, false},
+            {E_F, &f_poly, false}, {E_TABLE, &table_poly, false}, {E_TABLENEXT, &table_poly, true}};
+#pragma omp parallel for schedule(dynamic, 1)
+        for (int j = 0; j < NUM_EVAL; j++) e[jobs[j].slot] = poly_eval(*jobs[j].poly, jobs[j].shifted ? zs : ch.z);
+    }
     Fr vanishing = dom.evaluate_vanishing(ch.z);
     Fr z_to_n = vanishing + Fr::one();
     Fr l1_eval = vanishing * (Fr::from_u64(n) * (ch.z - Fr::one())).inverse();  // proof.rs:647-658
@@ -537,6 +557,7 @@ static inline ProofO prove(const ProverInput& in, Challenges* ch_out = nullptr) 
         for (int k = 0; k < 10; k++) tr.append_fr(cl[k], e[E_QARITH + k]);
     }
 
+    clk.lap("5b linearisation");
     // 6. openings
     ch.aw = tr.challenge_scalar("aggregate_witness");
     proof.comm[C_AW] = kzg_open(srs,
@@ -545,6 +566,7 @@ static inline ProofO prove(const ProverInput& in, Challenges* ch_out = nullptr) 
                                 ch.z, ch.aw);
     ch.saw = tr.challenge_scalar("aggregate_witness");
     proof.comm[C_SAW] = kzg_open(srs, {&z_poly, &w_poly[0], &w_poly[1], &w_poly[3], &h1_poly, &z2_poly, &table_poly}, zs, ch.saw);
+    clk.lap("6 openings");
     if (ch_out) *ch_out = ch;
     return proof;
 }

@@ -1,0 +1,37 @@
+"""Whole-proof byte parity at the sizes where gen_proof takes its PRODUCTION route — precomputed MSM window tables,
+batch-affine bucket rounds, batched commitments, 3-pass NTTs (N >= 2^16): HEIGHT=10 (N = 2^17), 12 (2^19) and the
+benchmark size HEIGHT=15 (2^22).  The expected bytes are the CPU oracle's proofs pinned under tests/golden/ by
+tests/golden/make_golden_large.py (the oracle needs 15 s ... 10 min per proof, so it is not re-run here); the
+circuit front end (witness + selectors) is rebuilt from the same seeds."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _prove(pkg, lib, oracle, height):
+    oc = oracle_lib.OracleCircuit(oracle, height, 42, 7, 0, with_pk=False, with_srs=False)
+    ctx = pkg.ProverContext(oc.log_n, lib)
+    ctx.generate_srs(oc.tau())
+    ctx.preprocess(oc.selector_evals(), oc.tables())
+    circ = pkg.make_circuit(oc.cs_n, oc.lookup_len, oc.pi_pos, oc.q_lookup(), oc.pi_canonical(), *oc.wires())
+    proof = ctx.prove(circ).to_words()
+    again = ctx.prove(circ).to_words()
+    ctx.close()
+    oc.close()
+    return proof, again
+
+
+@pytest.mark.parametrize("height", [10, 12, 15])
+def test_gen_proof_equals_pinned_oracle_proof(pkg, gpu_lib, oracle, height):
+    path = os.path.join(G, "proof_height%d_w42_tau7.npy" % height)
+    if not os.path.exists(path):
+        pytest.skip("fixture %s not generated" % os.path.basename(path))
+    proof, again = _prove(pkg, gpu_lib, oracle, height)
+    assert np.array_equal(proof, again), "proof differs between two runs on the same context"
+    assert np.array_equal(proof, np.load(path)), "device proof differs from the pinned oracle proof"

@@ -153,6 +153,48 @@ def test_drop_in_gen_proof_symbol(pkg, gpu_lib, oracle):
     oc.close()
 
 
+def _ffi_inputs(pkg, oc):
+    names = pkg.PK_POLY_NAMES + pkg.PK_SIGMA_NAMES
+    keep = [oc.pk_coeffs(), oc.pk_evals(), oc.tables(), oc.linear_evaluations(), oc.v_h_coset_8n(), oc.srs()]
+    pk = pkg.make_prover_key(dict(zip(names, keep[0])), dict(zip(names, keep[1])), keep[2], keep[3], keep[4])
+    ck = pkg.CommitKeyC()
+    ck.powers_of_g = pkg.as_u64p(keep[5])
+    circ = pkg.make_circuit(oc.cs_n, oc.lookup_len, oc.pi_pos, oc.q_lookup(), oc.pi_canonical(), *oc.wires())
+    return circ, pk, ck, keep
+
+
+def test_gen_proof_cache_is_keyed_on_content(pkg, gpu_lib, oracle):
+    """The reference's harness clones the prover key for every proof and rebuilds powers_of_g per call
+    (benches/pnp_bench.rs:62-118, prover.rs:700-711): same key at new addresses must NOT re-upload, and a different key
+    arriving in recycled buffers must not be served from the cache."""
+    import time
+    oc_a = oracle_lib.OracleCircuit(oracle, 6, 42, 7, 0)
+    oc_b = oracle_lib.OracleCircuit(oracle, 6, 43, 7, 0)  # other witness seed: different wiring -> different sigmas
+    ref_a, _ = oc_a.prove()
+    ref_b, _ = oc_b.prove()
+    gpu_lib.zp_gen_proof_invalidate()
+    circ, pk, ck, keep = _ffi_inputs(pkg, oc_a)
+    t0 = time.perf_counter()
+    assert np.array_equal(pkg.gen_proof(circ, pk, ck, gpu_lib).to_words(), ref_a)
+    cold = time.perf_counter() - t0
+    # "pk.clone()": fresh buffers, same content
+    circ2, pk2, ck2, keep2 = _ffi_inputs(pkg, oc_a)
+    assert keep2[1][1].ctypes.data != keep[1][1].ctypes.data
+    t0 = time.perf_counter()
+    assert np.array_equal(pkg.gen_proof(circ2, pk2, ck2, gpu_lib).to_words(), ref_a)
+    warm = time.perf_counter() - t0
+    assert warm < cold, (warm, cold)
+    # another key written INTO the buffers of the first one (same addresses)
+    circ_b, pk_b, ck_b, keep_b = _ffi_inputs(pkg, oc_b)
+    for dst, src in zip(keep[0] + keep[1], keep_b[0] + keep_b[1]):
+        dst[...] = src
+    proof = pkg.gen_proof(circ_b, pk, ck, gpu_lib).to_words()
+    assert np.array_equal(proof, ref_b)
+    gpu_lib.zp_gen_proof_invalidate()
+    oc_a.close()
+    oc_b.close()
+
+
 def test_verifier_key_and_known_tau(pkg, gpu_lib, oracle):
     oc = oracle_lib.OracleCircuit(oracle, 4, 42, 7, 0)
     ctx = pkg.ProverContext(oc.log_n, gpu_lib)

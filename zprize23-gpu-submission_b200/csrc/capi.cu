@@ -3,6 +3,9 @@
 #include <chrono>
 #include <map>
 #include <mutex>
+#include <thread>
+#include <atomic>
+#include <algorithm>
 #ifndef ZP_EMU
 #include <cuda_profiler_api.h>
 #endif
@@ -27,7 +30,9 @@ struct BenchState {
     double msm_ms[6] = {0, 0, 0, 0, 0, 0};
 };
 std::map<zp_prover*, BenchState*> g_bench;
+std::mutex g_bench_mu;  // the map only; a BenchState belongs to its context (one thread per context)
 BenchState& bench_of(zp_prover* p) {
+    std::lock_guard<std::mutex> lock(g_bench_mu);
     auto it = g_bench.find(p);
     if (it == g_bench.end()) it = g_bench.emplace(p, new BenchState()).first;
     return *it->second;
@@ -55,10 +60,13 @@ zp_prover* zp_prover_create(int log_n) {
     return reinterpret_cast<zp_prover*>(p);
 }
 void zp_prover_destroy(zp_prover* p) {
-    auto it = g_bench.find(p);
-    if (it != g_bench.end()) {
-        delete it->second;
-        g_bench.erase(it);
+    {
+        std::lock_guard<std::mutex> lock(g_bench_mu);
+        auto it = g_bench.find(p);
+        if (it != g_bench.end()) {
+            delete it->second;
+            g_bench.erase(it);
+        }
     }
     delete P(p);
 }
@@ -94,6 +102,24 @@ int zp_prover_load_pk(zp_prover* p, const ProverKeyC* pk, const uint64_t* coeff_
 }
 int zp_prover_preprocess(zp_prover* p, const uint64_t* const* selector_evals, const uint64_t* const* tables) {
     return guard([&] { P(p)->preprocess(selector_evals, tables); });
+}
+int zp_prover_read_pk(zp_prover* p, int index, uint64_t* coeffs_out, uint64_t* evals_out) {
+    return guard([&] {
+        Prover* pr = P(p);
+        if (!pr->have_pk) throw std::runtime_error("zp_prover_read_pk: no prover key");
+        if (index < 0 || index >= PK_COUNT + 4) throw std::runtime_error("zp_prover_read_pk: index out of range");
+        if (index >= PK_COUNT) {  // lookup table column (N Fr) through coeffs_out
+            if (coeffs_out) ZP_CUDA(cudaMemcpy(coeffs_out, pr->table[index - PK_COUNT].p, pr->n * sizeof(fr_t), cudaMemcpyDeviceToHost));
+            return;
+        }
+        auto fetch = [&](uint64_t* dst, const DevBuf<fr_t>& src, size_t cnt) {
+            if (!dst) return;
+            if (src.p) ZP_CUDA(cudaMemcpy(dst, src.p, cnt * sizeof(fr_t), cudaMemcpyDeviceToHost));
+            else memset(dst, 0, cnt * sizeof(fr_t));  // identically-zero polynomials are not kept on the device
+        };
+        fetch(coeffs_out, pr->coeffs[index], pr->n);
+        fetch(evals_out, pr->evals[index], pr->n8);
+    });
 }
 int zp_prover_verifier_key(zp_prover* p, uint64_t* out) { return guard([&] { P(p)->verifier_key(out); }); }
 int zp_prover_prove(zp_prover* p, const CircuitC* c, ProofC* out) { return guard([&] { P(p)->prove(*c, out); }); }
@@ -137,35 +163,92 @@ int zp_prover_last_timing(zp_prover* p, double* out_ms, int n) {
 }
 
 // ---- the reference's own symbol -------------------------------------------------------------------
-// Keeps one resident context per (domain size, pk pointer set, ck pointer); a sampled content
-// fingerprint guards against the caller recycling the same addresses for a different key.
+// Keeps ONE resident context keyed on the CONTENT of the key material (domain size + a fingerprint of every prover-key
+// array, the lookup tables and the SRS), never on addresses: the reference's callers hand over fresh buffers on every
+// call (`pk.clone()` per proof in benches/pnp_bench.rs:70; `powers_of_g_` rebuilt per call in prover.rs:700-711), so the
+// same key arrives at different pointers, and recycled addresses may carry a different key.
+//   ZPRIZE_B200_PK_CACHE unset / "1": strided fingerprint — every 1021st element (and the last) of each array; ~1 ms
+//   ZPRIZE_B200_PK_CACHE = "full"   : every word of every array (23 GiB at N = 2^22: memory-bandwidth time, threads)
+//   ZPRIZE_B200_PK_CACHE = "0"      : no caching (upload per call, like the reference)
+// A caller that rewrites a few elements of a key IN PLACE between calls must use "full", "0" or zp_gen_proof_invalidate().
 namespace {
 struct CacheEntry {
     Prover* prover = nullptr;
-    ProverKeyC pk;
-    const uint64_t* ck = nullptr;
     int logn = 0;
     uint64_t fingerprint = 0;
 };
 CacheEntry g_cache;
 std::mutex g_cache_mu;
-uint64_t fingerprint_of(const ProverKeyC& pk, const CommitKeyC& ck, size_t n) {
-    uint64_t h = 0xcbf29ce484222325ULL;
-    auto mix = [&](const uint64_t* p, size_t words) {
-        for (size_t i = 0; i < words; i++) h = (h ^ p[i]) * 0x100000001b3ULL;
+
+// reference convention for the *_coeffs arrays (gen_proof.cuh:61-62,277-278,319-329): q_m, range, logic, fixed, variable
+// and q_lookup are never dereferenced; the others hold N elements
+const bool kCoeffUnreadable[PK_COUNT] = {true, false, false, false, false, false, false, false, false, false,
+                                         true, true, true, true, true, false, false, false, false};
+
+uint64_t hash_span(const uint64_t* p, size_t elems, size_t words_per_elem, size_t stride, uint64_t seed) {
+    uint64_t h = seed ^ 0xcbf29ce484222325ULL;
+    auto mix = [&](size_t e) {
+        const uint64_t* q = p + e * words_per_elem;
+        for (size_t w = 0; w < words_per_elem; w++) h = (h ^ q[w]) * 0x100000001b3ULL;
+        h ^= h >> 29;
     };
-    const uint64_t* arrays[] = {pk.q_l_evals, pk.q_r_evals, pk.q_o_evals, pk.q_c_evals, pk.q_arith_evals, pk.left_sigma_evals,
-                                pk.fourth_sigma_evals, pk.q_hl_evals};
-    for (const uint64_t* a : arrays) {
-        mix(a, 64);
-        mix(a + 4 * (4 * n + 17), 64);
-        mix(a + 4 * (8 * n - 16), 64);
+    for (size_t e = 0; e < elems; e += stride) mix(e);
+    if (elems && (elems - 1) % stride != 0) mix(elems - 1);
+    return h;
+}
+uint64_t fingerprint_of(const ProverKeyC& pk, const CommitKeyC& ck, size_t n, bool full) {
+    struct Span { const uint64_t* p; size_t elems, words; };
+    std::vector<Span> spans;
+    const uint64_t* ev[PK_COUNT] = {pk.q_m_evals, pk.q_l_evals, pk.q_r_evals, pk.q_o_evals, pk.q_4_evals, pk.q_c_evals,
+                                    pk.q_hl_evals, pk.q_hr_evals, pk.q_h4_evals, pk.q_arith_evals, pk.range_selector_evals,
+                                    pk.logic_selector_evals, pk.fixed_group_add_selector_evals,
+                                    pk.variable_group_add_selector_evals, pk.q_lookup_evals, pk.left_sigma_evals,
+                                    pk.right_sigma_evals, pk.out_sigma_evals, pk.fourth_sigma_evals};
+    const uint64_t* co[PK_COUNT] = {pk.q_m_coeffs, pk.q_l_coeffs, pk.q_r_coeffs, pk.q_o_coeffs, pk.q_4_coeffs, pk.q_c_coeffs,
+                                    pk.q_hl_coeffs, pk.q_hr_coeffs, pk.q_h4_coeffs, pk.q_arith_coeffs, pk.range_selector_coeffs,
+                                    pk.logic_selector_coeffs, pk.fixed_group_add_selector_coeffs,
+                                    pk.variable_group_add_selector_coeffs, pk.q_lookup_coeffs, pk.left_sigma_coeffs,
+                                    pk.right_sigma_coeffs, pk.out_sigma_coeffs, pk.fourth_sigma_coeffs};
+    for (int i = 0; i < PK_COUNT; i++) {
+        spans.push_back({ev[i], 8 * n, 4});
+        if (!kCoeffUnreadable[i]) spans.push_back({co[i], n, 4});
     }
-    mix(ck.powers_of_g, 48);
-    mix(ck.powers_of_g + 12 * (n - 4), 48);
+    for (const uint64_t* t : {pk.table1, pk.table2, pk.table3, pk.table4}) spans.push_back({t, n, 4});
+    spans.push_back({ck.powers_of_g, n, 12});
+    const size_t stride = full ? 1 : 1021;
+    std::vector<uint64_t> part;
+    if (!full) {
+        for (size_t i = 0; i < spans.size(); i++) part.push_back(hash_span(spans[i].p, spans[i].elems, spans[i].words, stride, i));
+    } else {
+        // every word: split each array into 16 MiB pieces hashed by a small pool of threads
+        struct Piece { const uint64_t* p; size_t elems, words; };
+        std::vector<Piece> pieces;
+        for (auto& sp : spans) {
+            const size_t per = ((size_t)16 << 20) / (8 * sp.words);
+            for (size_t o = 0; o < sp.elems; o += per) pieces.push_back({sp.p + o * sp.words, std::min(per, sp.elems - o), sp.words});
+        }
+        part.assign(pieces.size(), 0);
+        unsigned nt = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+        std::atomic<size_t> next{0};
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < nt; t++)
+            pool.emplace_back([&] {
+                for (size_t i; (i = next.fetch_add(1)) < pieces.size();)
+                    part[i] = hash_span(pieces[i].p, pieces[i].elems, pieces[i].words, 1, i);
+            });
+        for (auto& th : pool) th.join();
+    }
+    uint64_t h = 0x9e3779b97f4a7c15ULL ^ (uint64_t)n;
+    for (uint64_t v : part) h = (h ^ v) * 0x100000001b3ULL + (h >> 31);
     return h;
 }
 }  // namespace
+
+extern "C" void zp_gen_proof_invalidate(void) {
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    delete g_cache.prover;
+    g_cache.prover = nullptr;
+}
 
 ProofC gen_proof(CircuitC circuit, ProverKeyC pk, CommitKeyC ck) {
     ProofC proof;
@@ -173,16 +256,20 @@ ProofC gen_proof(CircuitC circuit, ProverKeyC pk, CommitKeyC ck) {
     try {
         if (!zp_device_available()) throw std::runtime_error("no CUDA device: libzprize_b200 has no CPU fallback");
         std::lock_guard<std::mutex> lock(g_cache_mu);
-        // domain size as the reference derives it (lib/PLONK/src/composer.cu:3-21)
+        // domain size as the reference derives it (lib/PLONK/src/composer.cu:3-21): next_pow2(max(n, lookup_len)).
+        // The caller's arrays hold 8 * that many elements, so a size this library cannot prove over is an error, never
+        // silently rounded to another domain.
         size_t bound = circuit.n > circuit.lookup_len ? circuit.n : circuit.lookup_len;
+        if (circuit.n == 0) throw std::runtime_error("gen_proof: empty circuit");
         int logn = ilog2(bound);
-        if (logn < 6) logn = 6;
+        if (logn < 6 || logn > 23)
+            throw std::runtime_error("gen_proof: domain size 2^" + std::to_string(logn) + " outside the supported range [2^6, 2^23]");
         size_t n = (size_t)1 << logn;
         const char* env = getenv("ZPRIZE_B200_PK_CACHE");
-        bool use_cache = !(env && env[0] == '0');
-        uint64_t fp = fingerprint_of(pk, ck, n);
-        bool hit = use_cache && g_cache.prover && g_cache.logn == logn && g_cache.ck == ck.powers_of_g &&
-                   memcmp(&g_cache.pk, &pk, sizeof(pk)) == 0 && g_cache.fingerprint == fp;
+        const bool use_cache = !(env && env[0] == '0');
+        const bool full = env && strcmp(env, "full") == 0;
+        uint64_t fp = use_cache ? fingerprint_of(pk, ck, n, full) : 0;
+        bool hit = use_cache && g_cache.prover && g_cache.logn == logn && g_cache.fingerprint == fp;
         if (!hit) {
             delete g_cache.prover;
             g_cache.prover = nullptr;
@@ -190,8 +277,6 @@ ProofC gen_proof(CircuitC circuit, ProverKeyC pk, CommitKeyC ck) {
             g_cache.prover = p;
             p->load_srs(ck.powers_of_g, n);
             p->load_pk(pk, nullptr);
-            g_cache.pk = pk;
-            g_cache.ck = ck.powers_of_g;
             g_cache.logn = logn;
             g_cache.fingerprint = fp;
         }
@@ -470,6 +555,36 @@ int zp_combine_split_host(zp_prover* p, const uint64_t* t, const uint64_t* f, si
         ZP_CUDA(cudaStreamSynchronize(pr->st));
     });
 }
+int zp_multiset_combine_split_host(zp_prover* p, const uint64_t* t, size_t nt, const uint64_t* f, size_t nf, uint64_t* h1, uint64_t* h2) {
+    return guard([&] {
+        Prover* pr = P(p);
+        if (nt == 0) throw std::runtime_error("combine_split: empty table");
+        const size_t n1 = (nt + nf + 1) / 2, n2 = (nt + nf) / 2;
+        DevBuf<fr_t> dt(nt), df(nf ? nf : 1), d1(n1), d2(n2 ? n2 : 1);
+        ZP_CUDA(cudaMemcpyAsync(dt.p, t, nt * sizeof(fr_t), cudaMemcpyHostToDevice, pr->st));
+        if (nf) ZP_CUDA(cudaMemcpyAsync(df.p, f, nf * sizeof(fr_t), cudaMemcpyHostToDevice, pr->st));
+        if (!combine_split(pr->CS, dt.p, nt, df.p, nf, d1.p, d2.p, pr->st))
+            throw std::runtime_error("combine_split: ElementNotIndexed (an element of f is not in t)");
+        ZP_CUDA(cudaMemcpyAsync(h1, d1.p, n1 * sizeof(fr_t), cudaMemcpyDeviceToHost, pr->st));
+        if (n2) ZP_CUDA(cudaMemcpyAsync(h2, d2.p, n2 * sizeof(fr_t), cudaMemcpyDeviceToHost, pr->st));
+        ZP_CUDA(cudaStreamSynchronize(pr->st));
+    });
+}
+int zp_multiset_compress_host(zp_prover* p, const uint64_t* const* columns, size_t n, const uint64_t* challenge, uint64_t* out) {
+    return guard([&] {
+        Prover* pr = P(p);
+        DevBuf<fr_t> c[4], o(n);
+        for (int k = 0; k < 4; k++) {
+            c[k].alloc(n);
+            ZP_CUDA(cudaMemcpyAsync(c[k].p, columns[k], n * sizeof(fr_t), cudaMemcpyHostToDevice, pr->st));
+        }
+        fr_t ch;
+        memcpy(ch.l, challenge, 32);
+        compress4(o.p, c[0].p, c[1].p, c[2].p, c[3].p, ch, n, pr->st);
+        ZP_CUDA(cudaMemcpyAsync(out, o.p, n * sizeof(fr_t), cudaMemcpyDeviceToHost, pr->st));
+        ZP_CUDA(cudaStreamSynchronize(pr->st));
+    });
+}
 int zp_prefix_product_host(zp_prover* p, const uint64_t* in, size_t n, uint64_t* out) {
     return guard([&] {
         Prover* pr = P(p);
@@ -513,6 +628,27 @@ int zp_bench_ntt(zp_prover* p, int kind, int log_n, int slot_in, int slot_out, i
         ZP_CUDA(cudaEventCreate(&e1));
         ZP_CUDA(cudaEventRecord(e0, pr->st));
         for (int i = 0; i < iters; i++) ntt_run(pr->T, pr->NS, (NttKind)kind, log_n, b.slot[slot_in].p, n, b.slot[slot_out].p, pr->st);
+        ZP_CUDA(cudaEventRecord(e1, pr->st));
+        ZP_CUDA(cudaEventSynchronize(e1));
+        float t = 0;
+        ZP_CUDA(cudaEventElapsedTime(&t, e0, e1));
+        *ms = t / iters;
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    });
+}
+int zp_bench_ntt_padded(zp_prover* p, int kind, int log_n, size_t n_in, int slot_in, int slot_out, int iters, double* ms) {
+    return guard([&] {
+        Prover* pr = P(p);
+        BenchState& b = bench_of(p);
+        size_t n = (size_t)1 << log_n;
+        if (n_in > n || b.slot[slot_in].n < n_in || b.slot[slot_out].n < n) throw std::runtime_error("zp_bench_ntt_padded: slots too small");
+        cudaEvent_t e0, e1;
+        ZP_CUDA(cudaEventCreate(&e0));
+        ZP_CUDA(cudaEventCreate(&e1));
+        ntt_run(pr->T, pr->NS, (NttKind)kind, log_n, b.slot[slot_in].p, n_in, b.slot[slot_out].p, pr->st);  // builds the tables
+        ZP_CUDA(cudaEventRecord(e0, pr->st));
+        for (int i = 0; i < iters; i++) ntt_run(pr->T, pr->NS, (NttKind)kind, log_n, b.slot[slot_in].p, n_in, b.slot[slot_out].p, pr->st);
         ZP_CUDA(cudaEventRecord(e1, pr->st));
         ZP_CUDA(cudaEventSynchronize(e1));
         float t = 0;

@@ -7,6 +7,7 @@
 #include <stdexcept>
 #include <string>
 #include <vector>
+#include <atomic>
 #ifndef ZP_EMU
 #include <cuda_runtime.h>
 #endif
@@ -31,7 +32,7 @@
 
 namespace zp {
 
-extern unsigned long long g_launch_count;  // kernels launched by this library (bench.py "gpu_launches")
+extern std::atomic<unsigned long long> g_launch_count;  // kernels launched by this library (bench.py "gpu_launches")
 
 // The reference exits the process on a CUDA failure (lib/caffe/common.hpp:23-30).  We throw; the C-ABI
 // layer turns the exception into an error code / message (and, for the by-value `gen_proof` symbol that

@@ -441,10 +441,10 @@ __global__ void cs_emit_counts_kernel(const uint32_t* __restrict__ table, size_t
     if (idx != HS_EMPTY) cnt[idx] = table[2 * s + 1];
 }
 // position p of the sorted union belongs to the bucket i with offs[i] <= p < offs[i+1]; even p -> h1, odd p -> h2
-__global__ void cs_expand_kernel(const fr_t* __restrict__ t, const uint32_t* __restrict__ offs, size_t n, fr_t* __restrict__ h1,
-                                 fr_t* __restrict__ h2) {
+__global__ void cs_expand_kernel(const fr_t* __restrict__ t, const uint32_t* __restrict__ offs, size_t n, size_t total,
+                                 fr_t* __restrict__ h1, fr_t* __restrict__ h2) {
     size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= 2 * n) return;
+    if (p >= total) return;
     size_t lo = 0, hi = n;  // largest i < n with offs[i] <= p
     while (hi - lo > 1) {
         size_t mid = (lo + hi) >> 1;
@@ -454,6 +454,10 @@ __global__ void cs_expand_kernel(const fr_t* __restrict__ t, const uint32_t* __r
     store_fr((p & 1) ? &h2[p >> 1] : &h1[p >> 1], v);
 }
 bool combine_split(CombineSplitScratch& S, const fr_t* t, const fr_t* f, size_t n, fr_t* h1, fr_t* h2, cudaStream_t st) {
+    return combine_split(S, t, n, f, n, h1, h2, st);
+}
+// general lengths: t has n elements, f has nf; h1 receives ceil((n + nf) / 2) elements, h2 floor((n + nf) / 2)
+bool combine_split(CombineSplitScratch& S, const fr_t* t, size_t n, const fr_t* f, size_t nf, fr_t* h1, fr_t* h2, cudaStream_t st) {
     size_t slots = 1;
     while (slots < 2 * n) slots <<= 1;
     if (S.table.n < 2 * slots) S.table.alloc(2 * slots);
@@ -467,14 +471,14 @@ bool combine_split(CombineSplitScratch& S, const fr_t* t, const fr_t* f, size_t 
     ZP_CUDA(cudaMemsetAsync(S.flag.p, 0, sizeof(uint32_t), st));
     ZP_LAUNCH(cs_zero_counts_kernel, ew_grid(slots), dim3(EW_BLOCK), 0, st, S.table.p, slots);
     ZP_LAUNCH(cs_insert_t_kernel, ew_grid(n), dim3(EW_BLOCK), 0, st, t, n, S.table.p, (uint32_t)(slots - 1));
-    ZP_LAUNCH(cs_count_f_kernel, ew_grid(n), dim3(EW_BLOCK), 0, st, f, n, t, S.table.p, (uint32_t)(slots - 1), S.flag.p);
+    if (nf) ZP_LAUNCH(cs_count_f_kernel, ew_grid(nf), dim3(EW_BLOCK), 0, st, f, nf, t, S.table.p, (uint32_t)(slots - 1), S.flag.p);
     ZP_LAUNCH(cs_emit_counts_kernel, ew_grid(slots), dim3(EW_BLOCK), 0, st, S.table.p, slots, S.cnt.p);
     u32_exclusive_scan(S.cnt.p, S.offs.p, n, S.tile_sum.p, st);
     uint32_t err = 0;
     ZP_CUDA(cudaMemcpyAsync(&err, S.flag.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     ZP_CUDA(cudaStreamSynchronize(st));
     if (err) return false;
-    ZP_LAUNCH(cs_expand_kernel, ew_grid(2 * n), dim3(EW_BLOCK), 0, st, t, S.offs.p, n, h1, h2);
+    ZP_LAUNCH(cs_expand_kernel, ew_grid(n + nf), dim3(EW_BLOCK), 0, st, t, S.offs.p, n, n + nf, h1, h2);
     return true;
 }
 

@@ -51,6 +51,7 @@ struct CombineSplitScratch {
     DevBuf<uint32_t> cnt, offs, tile_sum, flag;
 };
 bool combine_split(CombineSplitScratch& S, const fr_t* t, const fr_t* f, size_t n, fr_t* h1, fr_t* h2, cudaStream_t st);
+bool combine_split(CombineSplitScratch& S, const fr_t* t, size_t nt, const fr_t* f, size_t nf, fr_t* h1, fr_t* h2, cudaStream_t st);
 
 struct QuotientArgs {
     int logn;                 // log2 N (the 8N coset has 2^(logn+3) points)

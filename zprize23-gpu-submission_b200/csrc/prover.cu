@@ -9,7 +9,7 @@
 
 namespace zp {
 
-unsigned long long g_launch_count = 0;
+std::atomic<unsigned long long> g_launch_count{0};
 
 using host::Fr;
 using host::Fq;
@@ -53,11 +53,12 @@ struct PhaseTimer {
     }
 };
 enum { CAT_TOTAL = 0, CAT_NTT = 1, CAT_MSM = 2, CAT_QUOT = 3, CAT_OTHER = 4 };
-static PhaseTimer* g_timer = nullptr;
+// spans are recorded into the timer of the proof in flight on THIS context (Prover::timer; null outside prove_resident)
 struct Scope {
+    PhaseTimer* t;
     int id;
-    explicit Scope(int cat) : id(g_timer ? g_timer->begin(cat) : -1) {}
-    ~Scope() { if (g_timer && id >= 0) g_timer->end(id); }
+    Scope(PhaseTimer* timer, int cat) : t(timer), id(timer ? timer->begin(cat) : -1) {}
+    ~Scope() { if (t && id >= 0) t->end(id); }
 };
 
 // ---- context -----------------------------------------------------------------------------------
@@ -363,7 +364,7 @@ void Prover::commit(const fr_t* coeffs_dev, size_t ncoef, CommitmentC* out, Fq* 
 // Commitments to k polynomials of ncoef coefficients each (null pointer / ncoef == 0: the identity).  The MSMs of the
 // non-trivial members run as ONE batch; when sharded, the k partial sums of a rank travel in one all-gather.
 void Prover::commit_batch(const fr_t* const* coeffs_dev, int k, size_t ncoef, CommitmentC* const* outs, Fq* xs, Fq* ys, bool* infs) {
-    Scope sc(CAT_MSM);
+    Scope sc(timer, CAT_MSM);
     if (!srs.p) throw std::runtime_error("commit: no SRS loaded");
     if (k < 1 || k > MSM_MAX_BATCH) throw std::runtime_error("commit_batch: batch size out of range");
     std::vector<host::G1> res(k, host::G1::infinity());
@@ -418,6 +419,7 @@ static void put_fr(uint64_t* dst, const Fr& a) { memcpy(dst, a.v, 32); }
 
 void Prover::upload_witness(const CircuitC& c) {
     if (c.n > n || c.n == 0) throw std::runtime_error("zp_prover_prove: circuit size does not fit the domain");
+    if (c.intended_pi_pos >= n) throw std::runtime_error("zp_prover_prove: intended_pi_pos lies outside the domain");
     const size_t cn = (size_t)c.n;
     // ---- 0. witness upload (gen_proof.cuh:11-17, load.cu:311-345)
     ensure_work_buffers(false);
@@ -459,10 +461,10 @@ void Prover::prove_resident(ProofC* out) {
     if (!have_pk) throw std::runtime_error("zp_prover_prove: no prover key loaded");
     if (!srs.p) throw std::runtime_error("zp_prover_prove: no SRS loaded");
     if (!wit_n) throw std::runtime_error("zp_prover_prove_resident: no witness uploaded");
-    PhaseTimer timer(st);
-    g_timer = &timer;
-    struct TimerGuard { ~TimerGuard() { g_timer = nullptr; } } timer_guard;
-    int total_id = timer.begin(CAT_TOTAL);
+    PhaseTimer proof_timer(st);
+    timer = &proof_timer;
+    struct TimerGuard { Prover* p; ~TimerGuard() { p->timer = nullptr; } } timer_guard{this};
+    int total_id = proof_timer.begin(CAT_TOTAL);
     memset(out, 0, sizeof(ProofC));
     const size_t cn = wit_n;
     const bool lookup_on = wit_lookup_on;
@@ -488,7 +490,7 @@ void Prover::prove_resident(ProofC* out) {
         CommitmentC* wc[4];
         Fq x[4], y[4]; bool inf[4];
         for (int k = 0; k < 4; k++) {
-            { Scope s(CAT_NTT); ntt_run(T, NS, NTT_INV, logn, w_ev[k].p, n, w_poly[k].p, st); }
+            { Scope s(timer, CAT_NTT); ntt_run(T, NS, NTT_INV, logn, w_ev[k].p, n, w_poly[k].p, st); }
             wp[k] = w_poly[k].p;
             wc[k] = &comm[k];
         }
@@ -502,19 +504,19 @@ void Prover::prove_resident(ProofC* out) {
     {
         Fq x, y; bool inf;
         if (lookup_on) {
-            { Scope s(CAT_OTHER);
+            { Scope s(timer, CAT_OTHER);
               compress4(t_ev.p, table[0].p, table[1].p, table[2].p, table[3].p, D(zeta), n, st);
               query_f(f_ev.p, w_ev[0].p, w_ev[1].p, w_ev[2].p, w_ev[3].p, qlk_ev.p, cn, t_ev.p, D(zeta), n, st); }
-            { Scope s(CAT_NTT);
+            { Scope s(timer, CAT_NTT);
               ntt_run(T, NS, NTT_INV, logn, t_ev.p, n, table_poly.p, st);
               ntt_run(T, NS, NTT_INV, logn, f_ev.p, n, f_poly.p, st); }
             commit(f_poly.p, n, &comm[5], &x, &y, &inf);
             tr.append_point("f", x, y, inf);
             // h1, h2 = combine_split(t, f) on the device (hash table keyed by the table value, ordered by first occurrence)
-            { Scope s(CAT_OTHER);
+            { Scope s(timer, CAT_OTHER);
               if (!combine_split(CS, t_ev.p, f_ev.p, n, h1_ev.p, h2_ev.p, st))
                   throw std::runtime_error("lookup: query element not in table (Error::ElementNotIndexed)"); }
-            { Scope s(CAT_NTT);
+            { Scope s(timer, CAT_NTT);
               ntt_run(T, NS, NTT_INV, logn, h1_ev.p, n, h1_poly.p, st);
               ntt_run(T, NS, NTT_INV, logn, h2_ev.p, n, h2_poly.p, st); }
             commit(h1_poly.p, n, &comm[6], &x, &y, &inf);
@@ -546,21 +548,21 @@ void Prover::prove_resident(ProofC* out) {
     {
         const fr_t* wp[4] = {w_ev[0].p, w_ev[1].p, w_ev[2].p, w_ev[3].p};
         const fr_t* sp[4] = {sigma_h[0].p, sigma_h[1].p, sigma_h[2].p, sigma_h[3].p};
-        { Scope s(CAT_OTHER);
+        { Scope s(timer, CAT_OTHER);
           perm_num_den(num.p, den.p, wp, sp, D(beta), D(gamma), logn, T, st);
           ratio_inplace(num.p, den.p, comb.p, n, st);
           exclusive_prefix_product(PS, den.p, num.p, n, st); }
-        { Scope s(CAT_NTT); ntt_run(T, NS, NTT_INV, logn, num.p, n, z_poly.p, st); }
+        { Scope s(timer, CAT_NTT); ntt_run(T, NS, NTT_INV, logn, num.p, n, z_poly.p, st); }
         Fq x, y; bool inf;
         commit(z_poly.p, n, &comm[4], &x, &y, &inf);
         tr.append_point("z", x, y, inf);
     }
     if (lookup_on) {
-        { Scope s(CAT_OTHER);
+        { Scope s(timer, CAT_OTHER);
           lookup_num_den(num.p, den.p, f_ev.p, t_ev.p, h1_ev.p, h2_ev.p, D(delta), D(epsilon), n, st);
           ratio_inplace(num.p, den.p, comb.p, n, st);
           exclusive_prefix_product(PS, den.p, num.p, n, st); }
-        { Scope s(CAT_NTT); ntt_run(T, NS, NTT_INV, logn, num.p, n, z2_poly.p, st); }
+        { Scope s(timer, CAT_NTT); ntt_run(T, NS, NTT_INV, logn, num.p, n, z2_poly.p, st); }
         commit(z2_poly.p, n, &comm[8]);
     } else {
         // every lookup ratio is (1+d) e * e(1+d) / (e(1+d))^2 = 1  =>  z2 = 1 on H, z2(X) = 1
@@ -612,7 +614,7 @@ void Prover::prove_resident(ProofC* out) {
             jobs.push_back({h1_poly.p, h18.p});
             jobs.push_back({h2_poly.p, h28.p});
         }
-        { Scope s(CAT_NTT);
+        { Scope s(timer, CAT_NTT);
           if (!dist) {
               for (size_t k = 0; k < jobs.size(); k++) ntt_run(T, NS, NTT_COSET_FWD, logn + 3, jobs[k].in, n, jobs[k].out, st);
           } else {
@@ -663,26 +665,26 @@ void Prover::prove_resident(ProofC* out) {
         qa.coset_j = -1;
         qa.coset_lc = 0;
         if (!dist) {
-            { Scope s(CAT_QUOT); quotient_evals(qa, st); }
-            { Scope s(CAT_NTT); ntt_run(T, NS, NTT_COSET_INV, logn + 3, quot.p, n8, t_poly.p, st); }
+            { Scope s(timer, CAT_QUOT); quotient_evals(qa, st); }
+            { Scope s(timer, CAT_NTT); ntt_run(T, NS, NTT_COSET_INV, logn + 3, quot.p, n8, t_poly.p, st); }
         } else {
             {   // one fused pass over this rank's cosets (compact arrays in, compact quotient values out)
                 QuotientArgs qc = qa;
                 qc.i_count = (size_t)cpr * n;
                 qc.coset_j = shard_rank * cpr;
                 qc.coset_lc = ilog2((size_t)cpr);
-                Scope s(CAT_QUOT);
+                Scope s(timer, CAT_QUOT);
                 quotient_evals(qc, st);
             }
             for (int c = 0; c < cpr; c++) {
                 const int j = shard_rank * cpr + c;
-                Scope s(CAT_NTT);
+                Scope s(timer, CAT_NTT);
                 // P_j = coefficients of the quotient restricted to coset j: iNTT_N, * 7^-m (coset iNTT), * w_8N^(-j m)
                 fr_t* pj = pj8.p + (size_t)j * n;
                 ntt_run(T, NS, NTT_COSET_INV, logn, quot.p + (size_t)c * n, n, pj, st);
                 if (j) ntt_coset_shift(T, pj, pj, n, logn + 3, j, true, st);
             }
-            { Scope s(CAT_NTT);
+            { Scope s(timer, CAT_NTT);
               for (int r = 0; r < shard_world; r++)
                   if (dev_bcast(dev_bcast_user, pj8.p + (size_t)r * cpr * n, (size_t)cpr * n * sizeof(fr_t), r) != 0)
                       throw std::runtime_error("device broadcast of the per-coset quotient coefficients failed");
@@ -746,7 +748,7 @@ void Prover::prove_resident(ProofC* out) {
             slots[cnt] = pl.slot;
             cnt++;
         }
-        { Scope s(CAT_OTHER); evaluate_many(PS, polys, points, cnt, n, results, st); }
+        { Scope s(timer, CAT_OTHER); evaluate_many(PS, polys, points, cnt, n, results, st); }
         for (int i = 0; i < cnt; i++) ev[slots[i]] = H(results[i]);
     }
     Fr vanishing = z_ch.pow_u64(n) - Fr::one();
@@ -814,7 +816,7 @@ void Prover::prove_resident(ProofC* out) {
             if (!t_zero[k]) term(t_poly.p + (size_t)k * n, Fr::zero() - (zp * vanishing));
             zp = zp * z_to_n;
         }
-        { Scope s(CAT_OTHER); lincomb(lin.p, lp.data(), ls.data(), (int)lp.size(), n, st); }
+        { Scope s(timer, CAT_OTHER); lincomb(lin.p, lp.data(), ls.data(), (int)lp.size(), n, st); }
     }
     // evaluations into the transcript (prover.rs:532-572) and the proof
     static const char* en[NUM_E] = {"a_eval", "b_eval", "c_eval", "d_eval", "left_sig_eval", "right_sig_eval", "out_sig_eval",
@@ -841,7 +843,7 @@ void Prover::prove_resident(ProofC* out) {
             }
             cj = cj * chal;
         }
-        { Scope s(CAT_OTHER);
+        { Scope s(timer, CAT_OTHER);
           lincomb(comb.p, lp.data(), ls.data(), (int)lp.size(), n, st);
           divide_by_linear(PS, comb.p, n, D(point), wit_out, st); }
     };
@@ -860,8 +862,8 @@ void Prover::prove_resident(ProofC* out) {
         commit_batch(op, 2, n, oc, x, y, inf);
     }
 
-    timer.end(total_id);
-    timer.collect(last_ms);
+    proof_timer.end(total_id);
+    proof_timer.collect(last_ms);
     last_ms[CAT_OTHER] = last_ms[CAT_TOTAL] - last_ms[CAT_NTT] - last_ms[CAT_MSM] - last_ms[CAT_QUOT];
 }
 

@@ -57,6 +57,7 @@ struct Prover {
     DevBuf<fr_t> cs_tmp, pj8;        // multi-GPU quotient round: shifted coefficients (N), per-coset quotient coefficients (8N)
     DevBuf<fr_t> num, den, lin, comb, wit, wit2;
     double last_ms[5] = {0, 0, 0, 0, 0};
+    PhaseTimer* timer = nullptr;     // phase timer of the proof in flight on this context
     // witness currently resident in w_ev / qlk_ev (set by upload_witness)
     size_t wit_n = 0;
     uint64_t wit_pi[4] = {0, 0, 0, 0};

@@ -144,6 +144,7 @@ def load_library(path=None):
         "zp_prover_read_srs": (ci, [vp, u64p, cs]),
         "zp_prover_load_pk": (ci, [vp, ctypes.POINTER(ProverKeyC), u64p]),
         "zp_prover_preprocess": (ci, [vp, ctypes.POINTER(u64p), ctypes.POINTER(u64p)]),
+        "zp_prover_read_pk": (ci, [vp, ci, u64p, u64p]),
         "zp_prover_verifier_key": (ci, [vp, u64p]),
         "zp_prover_prove": (ci, [vp, ctypes.POINTER(CircuitC), ctypes.POINTER(ProofC)]),
         "zp_prover_last_timing": (ci, [vp, dp, ci]),
@@ -163,10 +164,13 @@ def load_library(path=None):
         "zp_poly_divide_host": (ci, [vp, u64p, cs, u64p, u64p]),
         "zp_prefix_product_host": (ci, [vp, u64p, cs, u64p]),
         "zp_combine_split_host": (ci, [vp, u64p, u64p, cs, u64p, u64p]),
+        "zp_multiset_combine_split_host": (ci, [vp, u64p, cs, u64p, cs, u64p, u64p]),
+        "zp_multiset_compress_host": (ci, [vp, ctypes.POINTER(u64p), cs, u64p, u64p]),
         "zp_bench_alloc": (ci, [vp, ci, cs]),
         "zp_bench_upload": (ci, [vp, ci, u64p, cs]),
         "zp_bench_download": (ci, [vp, ci, u64p, cs]),
         "zp_bench_ntt": (ci, [vp, ci, ci, ci, ci, ci, dp]),
+        "zp_bench_ntt_padded": (ci, [vp, ci, ci, cs, ci, ci, ci, dp]),
         "zp_bench_msm": (ci, [vp, ci, cs, ci, dp, u64p]),
         "zp_bench_msm_batch": (ci, [vp, ci, cs, ci, ci, dp, u64p]),
         "zp_bench_msm_breakdown": (ci, [vp, dp]),
@@ -174,6 +178,7 @@ def load_library(path=None):
         "zp_proof_serialize": (ci, [ctypes.POINTER(ProofC), ctypes.c_char_p, cs, ctypes.POINTER(cs)]),
         "zp_proof_deserialize": (ci, [ctypes.c_char_p, cs, ctypes.POINTER(ProofC)]),
         "gen_proof": (ProofC, [CircuitC, ProverKeyC, CommitKeyC]),
+        "zp_gen_proof_invalidate": (None, []),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -183,13 +188,13 @@ def load_library(path=None):
     return lib
 
 
-EXPORTED_SYMBOLS = ["gen_proof", "zp_proof_serialize", "zp_proof_deserialize", "zp_last_error", "zp_launch_count", "zp_device_available", "zp_prover_create",
+EXPORTED_SYMBOLS = ["gen_proof", "zp_gen_proof_invalidate", "zp_proof_serialize", "zp_proof_deserialize", "zp_last_error", "zp_launch_count", "zp_device_available", "zp_prover_create",
                     "zp_prover_destroy", "zp_prover_set_label", "zp_profiler_range", "zp_prover_set_stream", "zp_prover_load_srs", "zp_prover_generate_srs",
-                    "zp_prover_read_srs", "zp_prover_load_pk", "zp_prover_preprocess", "zp_prover_verifier_key",
+                    "zp_prover_read_srs", "zp_prover_load_pk", "zp_prover_preprocess", "zp_prover_read_pk", "zp_prover_verifier_key",
                     "zp_prover_prove", "zp_prover_last_timing", "zp_prover_upload_witness", "zp_prover_prove_resident",
                     "zp_prover_collect_msm_stats", "zp_prover_msm_stats", "zp_prover_set_shard", "zp_prover_set_device_broadcast", "zp_ntt_host", "zp_ntt_sharded_host", "zp_bench_ntt_sharded", "zp_msm_host", "zp_msm_batch_host", "zp_msm_points_host",
-                    "zp_poly_eval_host", "zp_poly_divide_host", "zp_prefix_product_host", "zp_combine_split_host", "zp_bench_alloc",
-                    "zp_bench_upload", "zp_bench_download", "zp_bench_ntt", "zp_bench_msm", "zp_bench_msm_batch", "zp_bench_msm_breakdown",
+                    "zp_poly_eval_host", "zp_poly_divide_host", "zp_prefix_product_host", "zp_combine_split_host", "zp_multiset_combine_split_host", "zp_multiset_compress_host", "zp_bench_alloc",
+                    "zp_bench_upload", "zp_bench_download", "zp_bench_ntt", "zp_bench_ntt_padded", "zp_bench_msm", "zp_bench_msm_batch", "zp_bench_msm_breakdown",
                     "zp_bench_int_pipe"]
 
 
@@ -309,6 +314,13 @@ class ProverContext:
         if tables is not None:
             tb = (u64p * 4)(*[as_u64p(a) for a in tables])
         self._ck(self.lib.zp_prover_preprocess(self.h, arr, tb))
+
+    def read_pk(self, index, want_coeffs=True, want_evals=True):
+        """(coeffs [N,4] or None, evals [8N,4] or None) of prover-key polynomial `index` (ProverKeyC order; 19..22 = tables)."""
+        co = np.zeros((self.n, 4), dtype=np.uint64) if want_coeffs else None
+        ev = np.zeros((8 * self.n, 4), dtype=np.uint64) if (want_evals and index < 19) else None
+        self._ck(self.lib.zp_prover_read_pk(self.h, index, as_u64p(co), as_u64p(ev)))
+        return co, ev
 
     def verifier_key(self):
         out = np.zeros((23, 12), dtype=np.uint64)
@@ -437,6 +449,21 @@ class ProverContext:
         h1, h2 = np.zeros_like(t), np.zeros_like(t)
         self._ck(self.lib.zp_combine_split_host(self.h, as_u64p(t), as_u64p(f), t.shape[0], as_u64p(h1), as_u64p(h2)))
         return h1, h2
+
+    def multiset_combine_split(self, t, f):
+        """MultiSet::combine_split for |t| != |f| (lookup/multiset.rs:131-176)."""
+        nt, nf = t.shape[0], f.shape[0]
+        h1 = np.zeros(((nt + nf + 1) // 2, 4), dtype=np.uint64)
+        h2 = np.zeros(((nt + nf) // 2, 4), dtype=np.uint64)
+        self._ck(self.lib.zp_multiset_combine_split_host(self.h, as_u64p(t), nt, as_u64p(f), nf, as_u64p(h1), as_u64p(h2)))
+        return h1, h2
+
+    def multiset_compress(self, columns, challenge):
+        """MultiSet::compress (lookup/multiset.rs:207-213) of four columns with challenge `challenge`."""
+        arr = (u64p * 4)(*[as_u64p(c) for c in columns])
+        out = np.zeros_like(columns[0])
+        self._ck(self.lib.zp_multiset_compress_host(self.h, arr, columns[0].shape[0], as_u64p(challenge), as_u64p(out)))
+        return out
 
     def prefix_product(self, data):
         out = np.zeros_like(data)
