@@ -147,6 +147,16 @@ int zp_prover_load_pk(zp_prover* p, const ProverKeyC* pk, const uint64_t* coeff_
  * columns followed by the 4 sigma columns as evaluations on H (N Fr each, host memory, NULL = all
  * zero); tables[4] the padded lookup columns (N Fr each, NULL = all zero). */
 int zp_prover_preprocess(zp_prover* p, const uint64_t* const* selector_evals, const uint64_t* const* tables);
+/* The same with the PERMUTATION part of preprocessing on the device too (permutation/mod.rs:101-215): instead of the four
+ * sigma columns the caller passes the circuit's wire map — the reference's `Permutation::variable_map` flattened in
+ * insertion order: m entries, vars[i] = variable id (< n_vars), cells[i] = (gate << 2) | wire with wire 0 = left, 1 = right,
+ * 2 = output, 3 = fourth.  Every cell maps to the next cell of its variable (last -> first), unmapped cells to themselves;
+ * sigma_k(omega^i) = K_wire' * omega^gate' (K = 1, 7, 13, 17).  selector_evals15: the 15 selector columns (NULL = zero). */
+int zp_prover_preprocess_wiring(zp_prover* p, const uint64_t* const* selector_evals15, const uint32_t* vars, const uint32_t* cells,
+                                size_t m, uint32_t n_vars, const uint64_t* const* tables);
+/* Operator form: only the four sigma columns (N Fr each, host) from the wire map. */
+int zp_sigma_from_wiring_host(zp_prover* p, const uint32_t* vars, const uint32_t* cells, size_t m, uint32_t n_vars,
+                              uint64_t* const* sigma_out);
 /* Copy one prover-key polynomial back in the FFI layout: index 0..18 in ProverKeyC order (coeffs_out: N Fr, evals_out:
  * 8N Fr, either may be NULL), index 19..22 = lookup table columns (N Fr through coeffs_out).  With zp_prover_preprocess
  * this is the device twin of `preprocess_prover` (preprocess.rs:162-295) producing the ProverKeyC arrays. */
@@ -192,6 +202,31 @@ int zp_prover_last_timing(zp_prover* p, double* out_ms, int n);
 int zp_proof_serialize(const ProofC* proof, uint8_t* out, size_t capacity, size_t* written);
 /* Inverse of zp_proof_serialize: decompresses the points (y recovered from x, sign bit) — no subgroup check. */
 int zp_proof_deserialize(const uint8_t* bytes, size_t len, ProofC* out);
+
+/* ---- verifier (host side, real pairings) ------------------------------------------------------------------------
+ * `Proof::verify` of the reference (proof.rs:123-443; the two `KZG10::check` pairing equations at :414-441;
+ * `Verifier::verify`, verifier.rs:106-125) and a batch form that checks any number of proofs of the same circuit with ONE
+ * two-pairing product (random linear combination of all opening equations).
+ * commitments23: the 19 prover-key polynomial commitments in ProverKeyC order followed by the 4 table commitments (what
+ * zp_prover_verifier_key returns; the reference's VerifierKey holds the same points), 12 u64 each.
+ * beta_h: [tau] H of the SRS in G2, 24 u64 = x.c0 || x.c1 || y.c0 || y.c1 (Montgomery Fq), ark-poly-commit `vk.beta_h`.
+ * Public inputs: positions and Montgomery values (zero values are dropped like `PublicInputs` does, pi.rs:55-62). */
+typedef struct zp_verifier zp_verifier;
+const char* zp_verifier_last_error(void);
+zp_verifier* zp_verifier_create(uint64_t n, const uint64_t* commitments23, const uint64_t* beta_h);
+void zp_verifier_destroy(zp_verifier* v);
+int zp_verifier_set_label(zp_verifier* v, const char* label);
+/* *accepted = 1 iff both opening checks hold; *detail bit 0 = aggregate opening at z, bit 1 = shifted opening at z*omega */
+int zp_proof_verify(zp_verifier* v, const ProofC* proof, const uint64_t* pi_pos, const uint64_t* pi_vals, size_t n_pi, int* accepted,
+                    int* detail);
+/* count proofs, one public input each (pi_pos[i], pi_vals + 4 i) */
+int zp_proof_verify_batch(zp_verifier* v, const ProofC* proofs, size_t count, const uint64_t* pi_pos, const uint64_t* pi_vals,
+                          int* accepted);
+/* scalar * H (test SRS with a known trapdoor: beta_h = tau * H); scalar = Montgomery Fr */
+int zp_g2_mul_generator(const uint64_t* scalar, uint64_t* out24);
+/* prod_i e(P_i, Q_i): g1_points 12 u64 each, g2_points 24 u64 each; out72 = the GT element (Fq12, Montgomery limbs in
+ * tower order c0.c0.c0 .. c1.c2.c1), may be NULL */
+int zp_pairing_product(const uint64_t* g1_points, const uint64_t* g2_points, size_t count, uint64_t* out72, int* is_one);
 
 /* ---- operator entry points for the sweeps (function.cuh:45-113 equivalents) ------------------ */
 /* kind: 0 NTT, 1 iNTT, 2 coset-NTT (g = 7), 3 coset-iNTT; natural order in/out; host buffers. */

@@ -25,4 +25,7 @@ if [ -d "$REF" ]; then
         "$REF/PLONK/src/transcript/strobe.cpp" ref_shim.cpp -o _ref/libref_strobe.so
   fi
 fi
+if [ ! -f libsegv_trace.so ] || [ segv_trace.c -nt libsegv_trace.so ]; then
+  $CC -O1 -g -fPIC -shared -rdynamic segv_trace.c -o libsegv_trace.so
+fi
 echo "oracle build ok"

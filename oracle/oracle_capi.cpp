@@ -445,6 +445,16 @@ const uint64_t* zpo_ctx_linear_evaluations(void* h) { return (const uint64_t*)((
 const uint64_t* zpo_ctx_v_h_coset_8n(void* h) { return (const uint64_t*)((OracleCtx*)h)->pk.v_h_coset_8n.data(); }
 const uint64_t* zpo_ctx_srs(void* h) { return ((OracleCtx*)h)->srs_raw.data(); }
 const uint64_t* zpo_ctx_tau(void* h) { return ((OracleCtx*)h)->tau.v; }
+// the composer's wire map in insertion order (Permutation::variable_map flattened): m entries (variable, (gate << 2) | wire)
+uint64_t zpo_ctx_wiring_len(void* h) { return ((OracleCtx*)h)->cs.perm_log.size(); }
+uint64_t zpo_ctx_num_vars(void* h) { return ((OracleCtx*)h)->cs.var_vals.size(); }
+void zpo_ctx_wiring(void* h, uint32_t* vars, uint32_t* cells) {
+    const auto& log = ((OracleCtx*)h)->cs.perm_log;
+    for (size_t i = 0; i < log.size(); i++) {
+        vars[i] = log[i].first;
+        cells[i] = log[i].second;
+    }
+}
 
 // every gate equation of the synthetic circuit holds on the witness (sanity of the generator itself): arithmetic + PI
 // + the four custom widgets (separation challenges drawn at random) on every row, "next" = the following row, and

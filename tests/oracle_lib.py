@@ -31,7 +31,8 @@ class Oracle:
         L.zpo_ctx_new_kind.restype = vp
         L.zpo_ctx_new_kind.argtypes = [ci, ci, c64, c64, ci, ci, ci]
         L.zpo_ctx_free.argtypes = [vp]
-        for name in ["zpo_ctx_n", "zpo_ctx_lookup_len", "zpo_ctx_pi_pos"]:
+        L.zpo_ctx_wiring.argtypes = [vp, ctypes.c_void_p, ctypes.c_void_p]
+        for name in ["zpo_ctx_n", "zpo_ctx_lookup_len", "zpo_ctx_pi_pos", "zpo_ctx_wiring_len", "zpo_ctx_num_vars"]:
             getattr(L, name).restype = c64
             getattr(L, name).argtypes = [vp]
         L.zpo_ctx_logn.argtypes = [vp]
@@ -188,6 +189,13 @@ class OracleCircuit:
 
     def srs(self):
         return self._view(self.o.lib.zpo_ctx_srs(self.h), self.n, 12)
+
+    def wiring(self):
+        """(vars, cells, n_vars): the composer's wire map in insertion order; cell = (gate << 2) | wire."""
+        m = self.o.lib.zpo_ctx_wiring_len(self.h)
+        v, c = np.zeros(m, dtype=np.uint32), np.zeros(m, dtype=np.uint32)
+        self.o.lib.zpo_ctx_wiring(self.h, v.ctypes.data, c.ctypes.data)
+        return v, c, int(self.o.lib.zpo_ctx_num_vars(self.h))
 
     def tau(self):
         return self._view(self.o.lib.zpo_ctx_tau(self.h), 1).reshape(4)

@@ -169,7 +169,8 @@ def test_gen_proof_cache_is_keyed_on_content(pkg, gpu_lib, oracle):
     arriving in recycled buffers must not be served from the cache."""
     import time
     oc_a = oracle_lib.OracleCircuit(oracle, 6, 42, 7, 0)
-    oc_b = oracle_lib.OracleCircuit(oracle, 6, 43, 7, 0)  # other witness seed: different wiring -> different sigmas
+    oc_b = oracle_lib.OracleCircuit(oracle, 6, 42, 7, 8)  # 8 plookup rows + a table: other selectors, sigmas and tables, same N
+    assert oc_b.log_n == oc_a.log_n and not np.array_equal(oc_a.selector_evals()[15], oc_b.selector_evals()[15])
     ref_a, _ = oc_a.prove()
     ref_b, _ = oc_b.prove()
     gpu_lib.zp_gen_proof_invalidate()

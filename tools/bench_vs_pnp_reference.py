@@ -77,13 +77,16 @@ def main():
         n = 1 << lg
         x = orc.random_fr(1, n)
         path = os.path.join(args.tmp, "zp_ref_in_%d.npz" % lg)
-        ctx = pkg.ProverContext(min(max(lg, 6), 23), lib)
-        if not args.no_ntt and lg + 3 <= 26:
+        ctx = pkg.ProverContext(max(lg, 6), lib)  # > 2^23: operator-only context (SRS, MSM, NTT entry points)
+        if not args.no_ntt:
             np.savez(path, x=x)
-            ctx.bench_alloc(0, 8 * n)
-            ctx.bench_alloc(1, 8 * n)
+            big = 8 * n if lg + 3 <= 26 else n
+            ctx.bench_alloc(0, big)
+            ctx.bench_alloc(1, big)
             ctx.bench_upload(0, x)
             for kind in range(4):
+                if kind == 2 and lg + 3 > 26:
+                    continue
                 # ours: kind 2 = coset NTT of n coefficients zero-padded to 8n (what the quotient round runs)
                 our_lg = lg + 3 if kind == 2 else lg
                 if kind == 2:
@@ -106,7 +109,7 @@ def main():
             os.remove(path)
         if not args.no_msm:
             ctx.generate_srs(tau)
-            pts = ctx.read_srs(n) if lg <= 23 else None
+            pts = ctx.read_srs(n)
             ctx.bench_alloc(2, n)
             ctx.bench_upload(2, x)
             ours_ms, ours_out, _ = ctx.bench_msm(2, n, args.iters, 1)

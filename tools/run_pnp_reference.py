@@ -21,9 +21,14 @@ def main():
     ap.add_argument("--height", type=int, default=4)
     ap.add_argument("--out", required=True)
     ap.add_argument("--repeat", type=int, default=1)
+    ap.add_argument("--lib", default="libzprize_ref.so",
+                    help="libzprize_ref.so (unmodified) or libzprize_ref_patched.so (split_tx_poly bounds patch, see oracle/build_pnp_ref.sh)")
     args = ap.parse_args()
     pkg = load_package()
-    path = os.path.join(ROOT, "oracle", "_ref", "libzprize_ref.so")
+    trace = os.path.join(ROOT, "oracle", "libsegv_trace.so")
+    if os.path.exists(trace) and not os.environ.get("ZP_NO_SEGV_TRACE"):
+        ctypes.CDLL(trace)  # native backtrace on SIGSEGV: the reference's own code crashes above HEIGHT=4 on some runs
+    path = os.path.join(ROOT, "oracle", "_ref", args.lib)
     ref = ctypes.CDLL(path)
     ref.gen_proof.restype = pkg.ProofC
     ref.gen_proof.argtypes = [pkg.CircuitC, pkg.ProverKeyC, pkg.CommitKeyC]
@@ -45,9 +50,14 @@ def main():
         proof = ref.gen_proof(circ, pk, ck)
         print("reference gen_proof call %d: %.3f s" % (i, time.time() - t), flush=True)
     np.save(args.out, proof.to_words())
-    oracle_proof, _ = oc.prove()
+    pinned = os.path.join(ROOT, "tests", "golden", "proof_height%d_w42_tau7.npy" % args.height)
+    if os.path.exists(pinned):  # large sizes: the oracle's proof was pinned once (tests/golden/make_golden_large.py)
+        oracle_proof = np.load(pinned)
+    else:
+        oracle_proof, _ = oc.prove()
     np.save(args.out.replace(".npy", "_oracle.npy"), oracle_proof)
-    print("reference proof written", flush=True)
+    same = bool(np.array_equal(proof.to_words(), oracle_proof))
+    print("reference proof written; equals the oracle's proof: %s" % same, flush=True)
 
 
 if __name__ == "__main__":

@@ -267,23 +267,60 @@ void Prover::load_pk(const ProverKeyC& pk, const uint64_t* coeff_len) {
 }
 
 void Prover::preprocess(const uint64_t* const* selector_evals, const uint64_t* const* tables) {
+    preprocess_impl(selector_evals, PK_COUNT, nullptr, tables);
+}
+
+// sigma evaluations on H built on the device from the flattened wire map (wiring.cu; permutation/mod.rs:101-215)
+void Prover::sigma_from_wiring_host(const uint32_t* vars, const uint32_t* cells, size_t m, uint32_t n_vars, fr_t* const sigma_dev[4]) {
+    for (size_t i = 0; i < m; i++) {
+        if (vars[i] >= n_vars) throw std::runtime_error("wire map: variable id out of range");
+        if ((cells[i] >> 2) >= n) throw std::runtime_error("wire map: gate index outside the domain");
+    }
+    DevBuf<uint32_t> dv(m ? m : 1), dc(m ? m : 1);
+    if (m) {
+        ZP_CUDA(cudaMemcpyAsync(dv.p, vars, m * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        ZP_CUDA(cudaMemcpyAsync(dc.p, cells, m * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    }
+    sigma_from_wiring(WS, dv.p, dc.p, m, n_vars, logn, T, sigma_dev, st);
+    ZP_CUDA(cudaStreamSynchronize(st));
+}
+
+void Prover::preprocess_wiring(const uint64_t* const* selector_evals15, const uint32_t* vars, const uint32_t* cells, size_t m,
+                               uint32_t n_vars, const uint64_t* const* tables) {
+    if (msm_only) throw std::runtime_error("this context is larger than 2^23: SRS / MSM / NTT operators only, no prover key");
+    DevBuf<fr_t> sig[4];
+    fr_t* sp[4];
+    for (int k = 0; k < 4; k++) {
+        sig[k].alloc(n);
+        sp[k] = sig[k].p;
+    }
+    sigma_from_wiring_host(vars, cells, m, n_vars, sp);
+    preprocess_impl(selector_evals15, 15, sp, tables);
+}
+
+// selector_evals: n_host host columns (19: selectors + sigmas, or 15: selectors only with the sigmas in sigma_dev)
+void Prover::preprocess_impl(const uint64_t* const* selector_evals, int n_host, const fr_t* const* sigma_dev,
+                             const uint64_t* const* tables) {
     if (msm_only) throw std::runtime_error("this context is larger than 2^23: SRS / MSM / NTT operators only, no prover key");
     DevBuf<fr_t> stage(n);
     for (int i = 0; i < PK_COUNT; i++) {
-        if (!selector_evals[i]) {
-            coeffs[i].release();
-            evals[i].release();
-            continue;
+        const fr_t* src = nullptr;
+        if (i < n_host) {
+            if (selector_evals[i]) {
+                ZP_CUDA(cudaMemcpyAsync(stage.p, selector_evals[i], n * sizeof(fr_t), cudaMemcpyHostToDevice, st));
+                src = stage.p;
+            }
+        } else {
+            src = sigma_dev[i - PK_SIGL];
         }
-        ZP_CUDA(cudaMemcpyAsync(stage.p, selector_evals[i], n * sizeof(fr_t), cudaMemcpyHostToDevice, st));
-        if (all_zero(PS, stage.p, n, st)) {
+        if (!src || all_zero(PS, src, n, st)) {
             coeffs[i].release();
             evals[i].release();
             continue;
         }
         coeffs[i].alloc(n);
         evals[i].alloc(n8);
-        ntt_run(T, NS, NTT_INV, logn, stage.p, n, coeffs[i].p, st);                  // preprocess.rs:345-405
+        ntt_run(T, NS, NTT_INV, logn, src, n, coeffs[i].p, st);                      // preprocess.rs:345-405
         ntt_run(T, NS, NTT_COSET_FWD, logn + 3, coeffs[i].p, n, evals[i].p, st);    // preprocess.rs:171-246
         ZP_CUDA(cudaStreamSynchronize(st));
     }

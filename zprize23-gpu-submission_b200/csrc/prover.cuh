@@ -5,6 +5,7 @@
 #include "ntt.cuh"
 #include "msm.cuh"
 #include "poly.cuh"
+#include "wiring.cuh"
 #include "transcript.hpp"
 #include <string>
 
@@ -29,6 +30,7 @@ struct Prover {
     NttScratch NS;
     PolyScratch PS;
     CombineSplitScratch CS;
+    WiringScratch WS;
     MsmWorkspace MW;
 
     // ---- resident inputs (uploaded / built once, reused by every proof)
@@ -87,6 +89,10 @@ struct Prover {
     void generate_srs(const fr_t& tau, size_t npts);
     void load_pk(const ProverKeyC& pk, const uint64_t* coeff_len);
     void preprocess(const uint64_t* const* selector_evals, const uint64_t* const* tables);
+    void preprocess_wiring(const uint64_t* const* selector_evals15, const uint32_t* vars, const uint32_t* cells, size_t m,
+                           uint32_t n_vars, const uint64_t* const* tables);
+    void preprocess_impl(const uint64_t* const* selector_evals, int n_host, const fr_t* const* sigma_dev, const uint64_t* const* tables);
+    void sigma_from_wiring_host(const uint32_t* vars, const uint32_t* cells, size_t m, uint32_t n_vars, fr_t* const sigma_dev[4]);
     void finish_pk();
     void verifier_key(uint64_t* out23);
     void upload_witness(const CircuitC& c);

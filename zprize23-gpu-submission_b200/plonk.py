@@ -16,6 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libzprize_b200.so")
 
 u64p = ctypes.POINTER(ctypes.c_uint64)
+u32p = ctypes.POINTER(ctypes.c_uint32)
 
 
 class CommitmentC(ctypes.Structure):  # lib.rs:231-235
@@ -145,6 +146,8 @@ def load_library(path=None):
         "zp_prover_load_pk": (ci, [vp, ctypes.POINTER(ProverKeyC), u64p]),
         "zp_prover_preprocess": (ci, [vp, ctypes.POINTER(u64p), ctypes.POINTER(u64p)]),
         "zp_prover_read_pk": (ci, [vp, ci, u64p, u64p]),
+        "zp_prover_preprocess_wiring": (ci, [vp, ctypes.POINTER(u64p), u32p, u32p, cs, ctypes.c_uint32, ctypes.POINTER(u64p)]),
+        "zp_sigma_from_wiring_host": (ci, [vp, u32p, u32p, cs, ctypes.c_uint32, ctypes.POINTER(u64p)]),
         "zp_prover_verifier_key": (ci, [vp, u64p]),
         "zp_prover_prove": (ci, [vp, ctypes.POINTER(CircuitC), ctypes.POINTER(ProofC)]),
         "zp_prover_last_timing": (ci, [vp, dp, ci]),
@@ -177,6 +180,14 @@ def load_library(path=None):
         "zp_bench_int_pipe": (ci, [vp, ci, dp]),
         "zp_proof_serialize": (ci, [ctypes.POINTER(ProofC), ctypes.c_char_p, cs, ctypes.POINTER(cs)]),
         "zp_proof_deserialize": (ci, [ctypes.c_char_p, cs, ctypes.POINTER(ProofC)]),
+        "zp_verifier_last_error": (ctypes.c_char_p, []),
+        "zp_verifier_create": (vp, [ctypes.c_uint64, u64p, u64p]),
+        "zp_verifier_destroy": (None, [vp]),
+        "zp_verifier_set_label": (ci, [vp, ctypes.c_char_p]),
+        "zp_proof_verify": (ci, [vp, ctypes.POINTER(ProofC), u64p, u64p, cs, ctypes.POINTER(ci), ctypes.POINTER(ci)]),
+        "zp_proof_verify_batch": (ci, [vp, ctypes.POINTER(ProofC), cs, u64p, u64p, ctypes.POINTER(ci)]),
+        "zp_g2_mul_generator": (ci, [u64p, u64p]),
+        "zp_pairing_product": (ci, [u64p, u64p, cs, u64p, ctypes.POINTER(ci)]),
         "gen_proof": (ProofC, [CircuitC, ProverKeyC, CommitKeyC]),
         "zp_gen_proof_invalidate": (None, []),
     }
@@ -188,9 +199,9 @@ def load_library(path=None):
     return lib
 
 
-EXPORTED_SYMBOLS = ["gen_proof", "zp_gen_proof_invalidate", "zp_proof_serialize", "zp_proof_deserialize", "zp_last_error", "zp_launch_count", "zp_device_available", "zp_prover_create",
+EXPORTED_SYMBOLS = ["gen_proof", "zp_verifier_last_error", "zp_verifier_create", "zp_verifier_destroy", "zp_verifier_set_label", "zp_proof_verify", "zp_proof_verify_batch", "zp_g2_mul_generator", "zp_pairing_product", "zp_gen_proof_invalidate", "zp_proof_serialize", "zp_proof_deserialize", "zp_last_error", "zp_launch_count", "zp_device_available", "zp_prover_create",
                     "zp_prover_destroy", "zp_prover_set_label", "zp_profiler_range", "zp_prover_set_stream", "zp_prover_load_srs", "zp_prover_generate_srs",
-                    "zp_prover_read_srs", "zp_prover_load_pk", "zp_prover_preprocess", "zp_prover_read_pk", "zp_prover_verifier_key",
+                    "zp_prover_read_srs", "zp_prover_load_pk", "zp_prover_preprocess", "zp_prover_read_pk", "zp_prover_preprocess_wiring", "zp_sigma_from_wiring_host", "zp_prover_verifier_key",
                     "zp_prover_prove", "zp_prover_last_timing", "zp_prover_upload_witness", "zp_prover_prove_resident",
                     "zp_prover_collect_msm_stats", "zp_prover_msm_stats", "zp_prover_set_shard", "zp_prover_set_device_broadcast", "zp_ntt_host", "zp_ntt_sharded_host", "zp_bench_ntt_sharded", "zp_msm_host", "zp_msm_batch_host", "zp_msm_points_host",
                     "zp_poly_eval_host", "zp_poly_divide_host", "zp_prefix_product_host", "zp_combine_split_host", "zp_multiset_combine_split_host", "zp_multiset_compress_host", "zp_bench_alloc",
@@ -259,6 +270,73 @@ def gen_proof(circuit, pk, ck, lib=None):
     return lib.gen_proof(circuit, pk, ck)
 
 
+def proof_from_words(words):
+    """ProofC from its 2656-byte image (332 u64 words)."""
+    return ProofC.from_buffer_copy(np.ascontiguousarray(words, dtype=np.uint64).tobytes())
+
+
+def g2_mul_generator(scalar_words, lib=None):
+    lib = lib or load_library()
+    out = np.zeros(24, dtype=np.uint64)
+    if lib.zp_g2_mul_generator(as_u64p(np.ascontiguousarray(scalar_words, dtype=np.uint64)), as_u64p(out)) != 0:
+        raise ZprizeError(lib.zp_verifier_last_error().decode())
+    return out
+
+
+def pairing_product(g1_points, g2_points, lib=None):
+    """(GT element as 72 u64 words, is_one) of prod e(P_i, Q_i)."""
+    lib = lib or load_library()
+    g1 = np.ascontiguousarray(g1_points, dtype=np.uint64).reshape(-1, 12)
+    g2 = np.ascontiguousarray(g2_points, dtype=np.uint64).reshape(-1, 24)
+    out = np.zeros(72, dtype=np.uint64)
+    one = ctypes.c_int()
+    if lib.zp_pairing_product(as_u64p(g1), as_u64p(g2), g1.shape[0], as_u64p(out), ctypes.byref(one)) != 0:
+        raise ZprizeError(lib.zp_verifier_last_error().decode())
+    return out, one.value == 1
+
+
+class Verifier:
+    """`Proof::verify` with real pairings (host side of the library; needs no GPU)."""
+
+    def __init__(self, n, commitments23, beta_h, lib=None, label=None):
+        self.lib = lib or load_library()
+        c = np.ascontiguousarray(commitments23, dtype=np.uint64)
+        b = np.ascontiguousarray(beta_h, dtype=np.uint64)
+        self.h = self.lib.zp_verifier_create(n, as_u64p(c), as_u64p(b))
+        if not self.h:
+            raise ZprizeError(self.lib.zp_verifier_last_error().decode())
+        if label is not None and self.lib.zp_verifier_set_label(self.h, label) != 0:
+            raise ZprizeError(self.lib.zp_verifier_last_error().decode())
+
+    def close(self):
+        if self.h:
+            self.lib.zp_verifier_destroy(self.h)
+            self.h = None
+
+    def verify(self, proof, pi_pos, pi_val_mont):
+        """(accepted, detail): detail bit 0 = opening at z, bit 1 = opening at z * omega.  pi_val_mont None = no public input."""
+        if not isinstance(proof, ProofC):
+            proof = proof_from_words(proof)
+        acc, det = ctypes.c_int(), ctypes.c_int()
+        if pi_val_mont is None:
+            pos, val, cnt = np.zeros(1, np.uint64), np.zeros(4, np.uint64), 0
+        else:
+            pos, val, cnt = np.array([pi_pos], dtype=np.uint64), np.ascontiguousarray(pi_val_mont, dtype=np.uint64), 1
+        if self.lib.zp_proof_verify(self.h, ctypes.byref(proof), as_u64p(pos), as_u64p(val), cnt, ctypes.byref(acc),
+                                    ctypes.byref(det)) != 0:
+            raise ZprizeError(self.lib.zp_verifier_last_error().decode())
+        return acc.value == 1, det.value
+
+    def verify_batch(self, proofs, pi_pos, pi_vals_mont):
+        arr = (ProofC * len(proofs))(*[p if isinstance(p, ProofC) else proof_from_words(p) for p in proofs])
+        pos = np.ascontiguousarray(pi_pos, dtype=np.uint64)
+        val = np.ascontiguousarray(pi_vals_mont, dtype=np.uint64)
+        acc = ctypes.c_int()
+        if self.lib.zp_proof_verify_batch(self.h, arr, len(proofs), as_u64p(pos), as_u64p(val), ctypes.byref(acc)) != 0:
+            raise ZprizeError(self.lib.zp_verifier_last_error().decode())
+        return acc.value == 1
+
+
 class ProverContext:
     """Resident prover (extension of the FFI): SRS, prover key, twiddles and work buffers stay in HBM."""
 
@@ -314,6 +392,26 @@ class ProverContext:
         if tables is not None:
             tb = (u64p * 4)(*[as_u64p(a) for a in tables])
         self._ck(self.lib.zp_prover_preprocess(self.h, arr, tb))
+
+    def preprocess_wiring(self, selector_evals15, wire_vars, wire_cells, n_vars, tables=None):
+        """Preprocessing with the sigma polynomials built on the device from the wire map (uint32 arrays of equal length:
+        variable id and (gate << 2) | wire per entry, in the composer's insertion order)."""
+        arr = (u64p * 15)(*[as_u64p(a) for a in selector_evals15])
+        tb = None
+        if tables is not None:
+            tb = (u64p * 4)(*[as_u64p(a) for a in tables])
+        v = np.ascontiguousarray(wire_vars, dtype=np.uint32)
+        c = np.ascontiguousarray(wire_cells, dtype=np.uint32)
+        self._ck(self.lib.zp_prover_preprocess_wiring(self.h, arr, v.ctypes.data_as(u32p), c.ctypes.data_as(u32p), v.shape[0],
+                                                      n_vars, tb))
+
+    def sigma_from_wiring(self, wire_vars, wire_cells, n_vars):
+        v = np.ascontiguousarray(wire_vars, dtype=np.uint32)
+        c = np.ascontiguousarray(wire_cells, dtype=np.uint32)
+        out = [np.zeros((self.n, 4), dtype=np.uint64) for _ in range(4)]
+        arr = (u64p * 4)(*[as_u64p(a) for a in out])
+        self._ck(self.lib.zp_sigma_from_wiring_host(self.h, v.ctypes.data_as(u32p), c.ctypes.data_as(u32p), v.shape[0], n_vars, arr))
+        return out
 
     def read_pk(self, index, want_coeffs=True, want_evals=True):
         """(coeffs [N,4] or None, evals [8N,4] or None) of prover-key polynomial `index` (ProverKeyC order; 19..22 = tables)."""
