@@ -187,7 +187,7 @@ def test_gen_proof_cache_is_keyed_on_content(pkg, gpu_lib, oracle):
     assert warm < cold, (warm, cold)
     # another key written INTO the buffers of the first one (same addresses)
     circ_b, pk_b, ck_b, keep_b = _ffi_inputs(pkg, oc_b)
-    for dst, src in zip(keep[0] + keep[1], keep_b[0] + keep_b[1]):
+    for dst, src in zip(keep[0] + keep[1] + keep[2], keep_b[0] + keep_b[1] + keep_b[2]):
         dst[...] = src
     proof = pkg.gen_proof(circ_b, pk, ck, gpu_lib).to_words()
     assert np.array_equal(proof, ref_b)

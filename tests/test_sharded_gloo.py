@@ -22,7 +22,8 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, emu_path, out_dir, n_lookup=0):
+def _worker(rank, world, port, emu_path, out_dir, n_lookup=0, env=None):
+    os.environ.update(env or {})
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     sys.path.insert(0, ROOT)
     from conftest import load_package
@@ -64,12 +65,18 @@ def _worker(rank, world, port, emu_path, out_dir, n_lookup=0):
 import pytest  # noqa: E402
 
 
-@pytest.mark.parametrize("world,n_lookup", [(2, 0), (4, 12)])
-def test_sharded_msm_two_ranks(pkg, oracle, tmp_path, world, n_lookup):
+# second and third case: the precomputed-table route, where the ranks split the BUCKET range of the MSM (every rank walks
+# all points) — with batch-affine rounds forced on at this small size, and once in the old point-range mode
+BUCKETS = {"ZP_MSM_PRECOMP_MIN_LOG": "8", "ZP_MSM_BA_MIN_LOG": "8", "ZP_MSM_BA_ROUNDS": "2"}
+
+
+@pytest.mark.parametrize("world,n_lookup,env", [(2, 0, None), (4, 12, None), (2, 0, BUCKETS), (4, 12, BUCKETS),
+                                                (2, 0, dict(BUCKETS, ZP_SHARD_BUCKETS="0"))])
+def test_sharded_msm_two_ranks(pkg, oracle, tmp_path, world, n_lookup, env):
     import oracle_lib
     emu_path = pkg._build.build_emu()
     oracle_lib.load()
-    mp.spawn(_worker, args=(world, _free_port(), emu_path, str(tmp_path), n_lookup), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), emu_path, str(tmp_path), n_lookup, env), nprocs=world, join=True)
     oc = oracle_lib.OracleCircuit(oracle, 3, 42, 7, n_lookup)
     ref, _ = oc.prove()
     for r in range(world):

@@ -10,6 +10,12 @@
 //                  threads; long buckets are split so no digit distribution serialises
 //   6. reduce    : row / column sums of the bucket matrix, then weight * sum and a tree (msm_rowcol_kernel, msm_weighted_kernel)
 //   host         : with precomputed window tables one XYZZ point per member; otherwise Horner over the window sums; to affine
+// Multi-GPU (precomputed tables only): ranks split the BUCKETS, not the points.  A launch with cfg.bucket_lo / cfg.nbuckets
+// keeps only the digits whose bucket lies in [bucket_lo, bucket_lo + nbuckets) and numbers them locally; every rank walks all
+// scalars (cheap, HBM-bound) but accumulates 1/G of the bucket entries at the SAME window size and bucket load as one GPU
+// (point-range slices force c down — 16 windows instead of 13 at 2^19 points — and starve the batch-affine rounds).  The
+// reduction returns sum (j_local + 1) B_j and the plain sum T of the slice; the true weights are j_local + 1 + bucket_lo, so
+// the rank's share is  weighted + bucket_lo * T  (one short scalar multiplication on the host).
 // Order inside a bucket is not deterministic (atomics) but the group sum is exact, so the affine
 // result is bit-identical run to run.
 #include "msm.cuh"
@@ -49,7 +55,7 @@ MsmConfig msm_config_precomp(size_t n, size_t tab_stride) {
 
 static const int SCAN_TILE_FWD = 2048;
 // bucket matrix of the reduction (see msm_rowcol_kernel): 2^lw2 columns
-static int msm_reduce_lw2(const MsmConfig& cfg) { return cfg.c / 2; }  // nbuckets = 2^(c-1): W2 >= W1
+static int msm_reduce_lw2(const MsmConfig& cfg) { return (ilog2((size_t)cfg.nbuckets) + 1) / 2; }  // W2 >= W1; c / 2 for 2^(c-1) buckets
 static int msm_reduce_entries(const MsmConfig& cfg) { return (cfg.nbuckets >> msm_reduce_lw2(cfg)) + (1 << msm_reduce_lw2(cfg)); }
 static int msm_reduce_groups(const MsmConfig& cfg) { return (msm_reduce_entries(cfg) + 127) / 128; }
 
@@ -85,14 +91,14 @@ void MsmWorkspace::reserve(size_t n, const MsmConfig& cfg, int nbatch) {
     size_t nsets = (size_t)nbatch * cfg.nsets;
     size_t np = nsets * msm_reduce_groups(cfg);
     if (partial.n < np) partial.alloc(np);
-    if (final_sums.n < nsets) final_sums.alloc(nsets);
+    if (final_sums.n < 2 * nsets) final_sums.alloc(2 * nsets);
     if (rowcol.n < nsets * msm_reduce_entries(cfg)) rowcol.alloc(nsets * msm_reduce_entries(cfg));
-    if (np < nsets) np = nsets;
+    if (np < 2 * nsets) np = 2 * nsets;
     if (partial_host.size() < np) partial_host.resize(np);
 }
 
 // blockIdx.y = member of the batch (several scalar vectors over the same points, one bucket-set group each)
-__global__ void __launch_bounds__(256) msm_digits_kernel(MsmBatch batch, size_t n, int c, int nwin, int nbuckets,
+__global__ void __launch_bounds__(256) msm_digits_kernel(MsmBatch batch, size_t n, int c, int nwin, int nbuckets, uint32_t bucket_lo,
                                                          int one_set, uint32_t* __restrict__ digits, uint32_t* __restrict__ hist) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -119,6 +125,11 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(MsmBatch batch, size_t 
             carry = 1;
         } else {
             carry = 0;
+        }
+        // bucket slice of this launch: global bucket d - 1 -> local bucket d - 1 - bucket_lo, digits outside are dropped
+        if (d) {
+            const uint32_t g = d - 1 - bucket_lo;  // wraps below the slice
+            d = g < (uint32_t)nbuckets ? g + 1 : 0;
         }
         digits[(size_t)w * n + i] = d | (neg << 31);
         if (d) atomicAdd(&hist[(one_set ? 0 : (size_t)w * nbuckets) + d - 1], 1u);
@@ -464,6 +475,25 @@ __global__ void __launch_bounds__(128) msm_final_kernel(const xyzz_t* __restrict
     if (threadIdx.x == 0) store_xyzz(&final_out[blockIdx.x], sm[0]);
 }
 
+// total[set] = sum of the W2 column sums of the set (all buckets once)
+__global__ void __launch_bounds__(128) msm_plain_total_kernel(const xyzz_t* __restrict__ rc, int W1, int W2, xyzz_t* __restrict__ total) {
+    __shared__ xyzz_t sm[128];
+    const xyzz_t* C = rc + (size_t)blockIdx.x * (W1 + W2) + W1;
+    xyzz_t acc = xyzz_t::infinity();
+    for (int j = threadIdx.x; j < W2; j += blockDim.x) acc.add(load_xyzz(&C[j]));
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for (int d = blockDim.x >> 1; d >= 1; d >>= 1) {
+        if ((int)threadIdx.x < d) {
+            xyzz_t a = sm[threadIdx.x];
+            a.add(sm[threadIdx.x + d]);
+            sm[threadIdx.x] = a;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) store_xyzz(&total[blockIdx.x], sm[0]);
+}
+
 static void msm_launch_impl(MsmWorkspace& ws, const MsmConfig& cfg, const affine_t* points, const MsmBatch& batch, int nbatch, size_t n,
                             bool allow_ba, cudaStream_t st) {
     if (nbatch < 1 || nbatch > MSM_MAX_BATCH) throw std::runtime_error("msm: batch size out of range");
@@ -486,7 +516,7 @@ static void msm_launch_impl(MsmWorkspace& ws, const MsmConfig& cfg, const affine
     mark(0);
     if (n) {
         ZP_LAUNCH(msm_digits_kernel, dim3((unsigned)((n + 255) / 256), nbatch), dim3(256), 0, st, batch, n, cfg.c, cfg.nwin,
-                  cfg.nbuckets, cfg.tab_stride ? 1 : 0, ws.digits.p, ws.cursor.p);
+                  cfg.nbuckets, cfg.bucket_lo, cfg.tab_stride ? 1 : 0, ws.digits.p, ws.cursor.p);
     }
     mark(1);
     msm_scan(ws.cursor.p, ws.start.p, wb, ws.tile_sum.p, st);
@@ -501,13 +531,22 @@ static void msm_launch_impl(MsmWorkspace& ws, const MsmConfig& cfg, const affine
     const affine_t* pts = points;
     uint32_t pstride = cfg.pt_stride;  // the materialised partial sums of the batch-affine rounds are packed affine_t
     size_t est = wn;  // upper bound on the bucket entries still to be added
-    int rounds = (allow_ba && wn >= ws.ba_min_entries) ? ws.ba_rounds : 0;
+    const bool bucket_slice = cfg.nbuckets != (1 << (cfg.c - 1));
+    if (bucket_slice) {
+        // only the digits of this rank's bucket slice were kept: size the rounds by what is really there (one 4-byte read)
+        uint32_t total = 0;
+        ZP_CUDA(cudaMemcpyAsync(&total, ws.start.p + wb, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        ZP_CUDA(cudaStreamSynchronize(st));
+        est = total;
+    }
+    const size_t wn_eff = est;
+    int rounds = (allow_ba && wn_eff >= ws.ba_min_entries) ? ws.ba_rounds : 0;
     // leave >= 4 entries per bucket on average for the XYZZ pass (each round has a fixed cost of ~0.5 ms)
     if (!ws.ba_rounds_forced)
-        while (rounds > 0 && ((wn / wb) >> rounds) < 4) rounds--;
+        while (rounds > 0 && ((wn_eff / wb) >> rounds) < 4) rounds--;
     ws.ba_used = rounds > 0;
     if (rounds > 0) {
-        size_t cap0 = wn / 2 + wb;
+        size_t cap0 = wn_eff / 2 + wb;
         size_t up0 = (cap0 / (BA_K * BA_T) + 1) * BA_T;  // leaf groups (level-1 nodes of the inversion tree)
         if (ws.ba_pts[0].n < cap0) ws.ba_pts[0].alloc(cap0);
         if (rounds > 1 && ws.ba_pts[1].n < cap0 / 2 + wb) ws.ba_pts[1].alloc(cap0 / 2 + wb);
@@ -599,8 +638,14 @@ static void msm_launch_impl(MsmWorkspace& ws, const MsmConfig& cfg, const affine
     ZP_LAUNCH(msm_weighted_kernel, dim3((unsigned)(nsets * groups)), dim3(128), 0, st, ws.rowcol.p, cfg.nbuckets, lw2, groups,
               ws.partial.p);
     ZP_LAUNCH(msm_final_kernel, dim3(nsets), dim3(128), 0, st, ws.partial.p, groups, ws.final_sums.p);
+    if (cfg.bucket_lo) {
+        // plain sum of the slice's buckets = sum of its column sums rc[set][W1 .. W1 + W2)
+        const int W2 = 1 << lw2, W1 = cfg.nbuckets >> lw2;
+        ZP_LAUNCH(msm_plain_total_kernel, dim3(nsets), dim3(128), 0, st, ws.rowcol.p, W1, W2, ws.final_sums.p + nsets);
+    }
     mark(6);
-    ZP_CUDA(cudaMemcpyAsync(ws.partial_host.data(), ws.final_sums.p, (size_t)nsets * sizeof(xyzz_t), cudaMemcpyDeviceToHost, st));
+    ZP_CUDA(cudaMemcpyAsync(ws.partial_host.data(), ws.final_sums.p, (size_t)(cfg.bucket_lo ? 2 : 1) * nsets * sizeof(xyzz_t),
+                            cudaMemcpyDeviceToHost, st));
     if (ws.ba_used) {
         // entries the accumulate kernel saw (for the roofline accounting) + the degenerate-pair flag
         ZP_CUDA(cudaMemcpyAsync(&ws.ba_flag_host[1], run_begin + wb, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -658,6 +703,15 @@ std::vector<host::G1> msm_collect_batch(MsmWorkspace& ws, const MsmConfig& cfg, 
         host::G1 total = host::G1::infinity();
         if (cfg.nsets == 1) {
             total = host::G1::from_dev(ph[0]);  // precomputed tables: window weights are in the points
+            if (cfg.bucket_lo) {
+                // bucket slice: true weight of local bucket j is j + 1 + bucket_lo  =>  add bucket_lo * (plain sum of the slice)
+                host::G1 plain = host::G1::from_dev(ws.partial_host[(size_t)ws.last_nbatch + b]), acc = host::G1::infinity();
+                for (int bit = 31 - __builtin_clz(cfg.bucket_lo); bit >= 0; bit--) {
+                    acc.dbl_inplace();
+                    if ((cfg.bucket_lo >> bit) & 1) acc.add(plain);
+                }
+                total.add(acc);
+            }
         } else {
             for (int w = cfg.nwin - 1; w >= 0; w--) {
                 for (int k = 0; k < cfg.c; k++) total.dbl_inplace();

@@ -11,7 +11,8 @@ namespace zp {
 struct MsmConfig {
     int c;              // window bits
     int nwin;           // number of windows = ceil(256 / c)
-    int nbuckets;       // buckets per bucket set = 2^(c-1)
+    int nbuckets;       // buckets per bucket set accumulated by this launch: 2^(c-1), or a power-of-two slice of them
+    uint32_t bucket_lo = 0;  // first global bucket of that slice (multi-GPU sharding by BUCKET range, see msm.cu); 0 = all
     int nsets;          // bucket sets: nwin normally, 1 with precomputed window tables
     size_t tab_stride;  // 0, or the row stride of a precomputed table [w][i] = 2^(c w) * P_i
     uint32_t pt_stride; // bytes between consecutive points: 96 (FFI affine_t) or 128 (padded table entries)
@@ -82,7 +83,7 @@ struct MsmWorkspace {
     size_t seg = 0;            // points per work segment (2x the mean bucket load, >= 32)
     DevBuf<xyzz_t> rowcol;     // [nsets][W1 + W2] row / column sums of the bucket matrix (bucket reduction, step 1)
     DevBuf<xyzz_t> partial;    // [nsets][groups] weighted partial sums (bucket reduction, step 2)
-    DevBuf<xyzz_t> final_sums; // [nsets] per-set sums (what returns to the host)
+    DevBuf<xyzz_t> final_sums; // [2 * nsets] per-set weighted sums, then per-set plain sums (what returns to the host)
     std::vector<xyzz_t> partial_host;
     // optional per-stage timing (bench only): digits, scan, scatter, batch-affine rounds, accumulate (+ folds), reduce
     bool timing = false;

@@ -65,6 +65,8 @@ struct Scope {
 Prover::Prover(int logn_) : logn(logn_), n((size_t)1 << logn_), n8((size_t)8 << logn_) {
     const char* pc = getenv("ZP_MSM_PRECOMP");
     if (pc && pc[0] == '0') use_precomp = false;
+    const char* sb = getenv("ZP_SHARD_BUCKETS");
+    if (sb && sb[0] == '0') shard_buckets = false;
     const char* pm = getenv("ZP_MSM_PRECOMP_MIN_LOG");
     if (pm) precomp_min = (size_t)1 << atoi(pm);
     if (logn < 6 || logn > NTT_LMAX) throw std::runtime_error("zp_prover_create: log_n must be in [6, 26]");
@@ -352,8 +354,17 @@ void Prover::finish_pk() {
 host::G1 Prover::msm_over_srs(const fr_t* scalars_dev, size_t lo, size_t hi, size_t slice) {
     return msm_over_srs_batch(&scalars_dev, 1, lo, hi, slice)[0];
 }
-// the same for k scalar vectors at once (one MSM pipeline, see MsmBatch)
-std::vector<host::G1> Prover::msm_over_srs_batch(const fr_t* const* scalars_dev, int k, size_t lo, size_t hi, size_t slice) {
+// true when a sharded commitment of ncoef coefficients splits the BUCKETS of the precomputed-table MSM across the ranks
+// (every rank walks all points; see msm.cu) instead of the point range
+bool Prover::shard_by_buckets(size_t ncoef) const {
+    if (shard_world <= 1 || (shard_world & (shard_world - 1)) || !shard_buckets || !use_precomp || ncoef < precomp_min) return false;
+    MsmConfig c = msm_config_precomp(srs.n, srs.n);
+    return c.nbuckets / shard_world >= 256;
+}
+// the same for k scalar vectors at once (one MSM pipeline, see MsmBatch); bucket_world > 1: only the bucket slice of
+// bucket_rank (precomputed-table route)
+std::vector<host::G1> Prover::msm_over_srs_batch(const fr_t* const* scalars_dev, int k, size_t lo, size_t hi, size_t slice,
+                                                 int bucket_rank, int bucket_world) {
     MsmConfig cfg = msm_config_for(hi - lo);
     const affine_t* base = srs.p + lo;
     if (use_precomp && hi - lo >= precomp_min) {
@@ -367,13 +378,19 @@ std::vector<host::G1> Prover::msm_over_srs_batch(const fr_t* const* scalars_dev,
         }
         cfg = tab_cfg;
         base = reinterpret_cast<const affine_t*>(srs_tab.p);
+        if (bucket_world > 1) {
+            cfg.nbuckets = tab_cfg.nbuckets / bucket_world;
+            cfg.bucket_lo = (uint32_t)bucket_rank * (uint32_t)cfg.nbuckets;
+        }
+    } else if (bucket_world > 1) {
+        throw std::runtime_error("msm: bucket sharding needs the precomputed-table route");
     }
     msm_launch_batch(MW, cfg, base, scalars_dev, k, hi - lo, st);
     std::vector<host::G1> r = msm_collect_batch(MW, cfg, st);
     if (MW.timing) {
         msm_acc_ms += MW.last_ms[3] + MW.last_ms[4];  // bucket accumulation: batch-affine rounds + XYZZ accumulate + folds
         for (int i = 0; i < 6; i++) msm_all_ms += MW.last_ms[i];
-        double entries = (double)(hi - lo) * cfg.nwin * k;
+        double entries = (double)(hi - lo) * cfg.nwin * k / (bucket_world > 1 ? bucket_world : 1);
         msm_mads += 10.0 * 588.0 * entries;  // 10 * 588 * M * W
         // multiply-adds actually issued: a batch-affine addition costs ~6.2 Fq products (3 for the shared inversion incl.
         // the tree levels above the leaves, 3 for the chord), an XYZZ mixed addition 10
@@ -409,15 +426,22 @@ void Prover::commit_batch(const fr_t* const* coeffs_dev, int k, size_t ncoef, Co
     for (int i = 0; i < k; i++)
         if (coeffs_dev[i] && ncoef) live.push_back(i);
     if (!live.empty()) {
-        // point-range shard of this rank (the whole range when world == 1)
-        size_t chunk = (ncoef + shard_world - 1) / shard_world;
-        size_t lo = std::min(ncoef, (size_t)shard_rank * chunk), hi = std::min(ncoef, lo + chunk);
         const int m = (int)live.size();
         std::vector<host::G1> part(m, host::G1::infinity());
-        if (hi > lo) {
+        if (shard_by_buckets(ncoef)) {
+            // bucket-range shard: all points, this rank's slice of the 2^(c-1) buckets (same window size as one GPU)
             std::vector<const fr_t*> sp(m);
-            for (int j = 0; j < m; j++) sp[j] = coeffs_dev[live[j]] + lo;
-            part = msm_over_srs_batch(sp.data(), m, lo, hi, std::min(chunk, srs.n - lo));
+            for (int j = 0; j < m; j++) sp[j] = coeffs_dev[live[j]];
+            part = msm_over_srs_batch(sp.data(), m, 0, ncoef, srs.n, shard_rank, shard_world);
+        } else {
+            // point-range shard of this rank (the whole range when world == 1)
+            size_t chunk = (ncoef + shard_world - 1) / shard_world;
+            size_t lo = std::min(ncoef, (size_t)shard_rank * chunk), hi = std::min(ncoef, lo + chunk);
+            if (hi > lo) {
+                std::vector<const fr_t*> sp(m);
+                for (int j = 0; j < m; j++) sp[j] = coeffs_dev[live[j]] + lo;
+                part = msm_over_srs_batch(sp.data(), m, lo, hi, std::min(chunk, srs.n - lo));
+            }
         }
         if (shard_world > 1) {
             if (!allgather) throw std::runtime_error("commit: sharded prover without an all-gather callback");

@@ -76,6 +76,7 @@ struct Prover {
     // sharded by point range; the per-rank partial sums (one XYZZ point, 192 B) are exchanged through the
     // caller-supplied all-gather (torch.distributed / NCCL in bench.py) and folded in rank order.
     int shard_rank = 0, shard_world = 1;
+    bool shard_buckets = true;  // precomputed-table MSMs: split the bucket range across ranks, not the points (ZP_SHARD_BUCKETS=0: points)
     zp_allgather_fn allgather = nullptr;
     void* allgather_user = nullptr;
     zp_dev_broadcast_fn dev_bcast = nullptr;
@@ -100,7 +101,9 @@ struct Prover {
     void prove(const CircuitC& c, ProofC* out);
 
     host::G1 msm_over_srs(const fr_t* scalars_dev, size_t lo, size_t hi, size_t slice);
-    std::vector<host::G1> msm_over_srs_batch(const fr_t* const* scalars_dev, int k, size_t lo, size_t hi, size_t slice);
+    std::vector<host::G1> msm_over_srs_batch(const fr_t* const* scalars_dev, int k, size_t lo, size_t hi, size_t slice,
+                                             int bucket_rank = 0, int bucket_world = 1);
+    bool shard_by_buckets(size_t ncoef) const;
     void commit_batch(const fr_t* const* coeffs_dev, int k, size_t ncoef, CommitmentC* const* outs, host::Fq* xs, host::Fq* ys, bool* infs);
     // commit to n coefficients (Montgomery) on the device; returns affine point (host)
     void commit(const fr_t* coeffs_dev, size_t ncoef, CommitmentC* out, host::Fq* ox = nullptr, host::Fq* oy = nullptr, bool* oinf = nullptr);
