@@ -303,8 +303,14 @@ def main():
             t = torch.as_tensor(_DevMem(ptr, nbytes), device="cuda")
             dist.broadcast(t, src=root)  # NCCL over NVLink, ordered on the prover's (= torch's current) stream
 
+        def dev_allgather(ptr, nbytes):
+            whole = torch.as_tensor(_DevMem(ptr, nbytes * world), device="cuda")
+            dist.all_gather_into_tensor(whole, whole[rank * nbytes:(rank + 1) * nbytes])  # in place (NCCL allows send inside recv)
+
         if os.environ.get("ZP_DIST_NTT", "1") != "0":
             ctx.set_device_broadcast(dev_bcast)
+            if os.environ.get("ZP_DEV_ALLGATHER", "1") != "0":
+                ctx.set_device_allgather(dev_allgather)
 
     # witness in PINNED host memory (what the e2e leg copies from every step)
     def pinned(a):

@@ -169,6 +169,17 @@ int zp_prover_prove(zp_prover* p, const CircuitC* circuit, ProofC* out);
  * any number of times with every input already resident. */
 int zp_prover_upload_witness(zp_prover* p, const CircuitC* circuit);
 int zp_prover_prove_resident(zp_prover* p, ProofC* out);
+/* Witness synthesis ON THE DEVICE for the Poseidon-Merkle circuit family (the reference runs the gadget on one CPU thread,
+ * 9.4 s at HEIGHT=15: constraint_system/hash.rs:20-127, plonk-hashing/src/poseidon/zprize_constraints.rs:141-265,
+ * merkle-tree/src/lib.rs:41-59): leaves = 2^(height-1) Fr, hash_params = 3x3 MDS (row-major) || 3 pre-round keys || 63x3 round
+ * constants, blinding = the 8 values of the two blinding rows (all Montgomery).  Leaves the four wire columns resident
+ * (cs.n = 4 + 193 (2^(height-1) - 1) + 1 rows, public input -root at the last gate) for zp_prover_prove_resident;
+ * root_out (optional) receives the root. */
+int zp_prover_synthesize_merkle_witness(zp_prover* p, int height, const uint64_t* leaves, const uint64_t* hash_params,
+                                        const uint64_t* blinding, uint64_t* root_out);
+/* rows of the resident witness / copy of wire column 0..3 (rows x 4 u64) back to the host */
+uint64_t zp_prover_witness_rows(zp_prover* p);
+int zp_prover_read_witness(zp_prover* p, int wire, uint64_t* out);
 /* Per-proof statistics of the MSM bucket-accumulation kernel (the dominant kernel): enable, then after a
  * proof read out4 = { sum of kernel ms, launches, algorithmic 32-bit multiply-adds (10*588*M*W),
  * sum of all MSM kernel ms }. */
@@ -189,6 +200,12 @@ int zp_prover_set_shard(zp_prover* p, int rank, int world, zp_allgather_fn allga
  * the fused quotient pass is split by index range (each rank's slice broadcast to the others). */
 typedef int (*zp_dev_broadcast_fn)(void* user, void* dev_ptr, size_t bytes, int root);
 int zp_prover_set_device_broadcast(zp_prover* p, zp_dev_broadcast_fn bcast, void* user);
+/* Optional third hook: IN-PLACE all-gather of device memory — rank r's block [r * bytes_per_rank, (r + 1) * bytes_per_rank) of
+ * `dev_base` is sent to every rank, ordered on the prover's stream (ncclAllGather / torch all_gather_into_tensor).  When
+ * set it replaces the per-owner broadcasts of the witness slices and of the per-coset quotient coefficients by ONE
+ * collective each. */
+typedef int (*zp_dev_allgather_fn)(void* user, void* dev_base, size_t bytes_per_rank);
+int zp_prover_set_device_allgather(zp_prover* p, zp_dev_allgather_fn allgather, void* user);
 /* Device-milliseconds of the phases of the last proof: [0] total, [1] NTT, [2] MSM, [3] quotient,
  * [4] other (CUDA events on the prover's stream). */
 int zp_prover_last_timing(zp_prover* p, double* out_ms, int n);

@@ -46,8 +46,12 @@ src = open(sys.argv[1]).read()
 old = "caffe_gpu_memcpy(t_.size(), t_gpu + i*t_.size(), t_x_gpu);"
 new = ("{ size_t off = (size_t)i * t_.size(); size_t avail = off < t_poly.size() ? t_poly.size() - off : 0; "
        "size_t cnt = avail < t_.size() ? avail : t_.size(); "
+       "cudaPointerAttributes pa, pb; cudaPointerGetAttributes(&pa, (char*)t_gpu + off); cudaPointerGetAttributes(&pb, t_x_gpu); "
        "if (i == 0) fprintf(stderr, \"[ref-patch] split_tx_poly: t_poly holds %zu bytes, 8 slices need %zu\\n\", t_poly.size(), 8 * t_.size()); "
-       "cudaMemset(t_x_gpu, 0, t_.size()); if (cnt) caffe_gpu_memcpy(cnt, (char*)t_gpu + off, t_x_gpu); }")
+       "fprintf(stderr, \"[ref-patch] slice %d: src %p (memory type %d) dst %p (memory type %d) bytes %zu\\n\", i, (char*)t_gpu + off, (int)pa.type, t_x_gpu, (int)pb.type, cnt); "
+       "cudaError_t e1 = cudaMemset(t_x_gpu, 0, t_.size()); "
+       "cudaError_t e2 = cnt ? cudaMemcpy(t_x_gpu, (char*)t_gpu + off, cnt, cudaMemcpyDeviceToDevice) : cudaSuccess; "
+       "if (e1 != cudaSuccess || e2 != cudaSuccess) fprintf(stderr, \"[ref-patch] memset: %s, memcpy: %s\\n\", cudaGetErrorString(e1), cudaGetErrorString(e2)); }")
 assert old in src
 open(sys.argv[2], "w").write(src.replace(old, new))
 PYEOF

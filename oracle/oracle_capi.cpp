@@ -456,6 +456,24 @@ void zpo_ctx_wiring(void* h, uint32_t* vars, uint32_t* cells) {
     }
 }
 
+// inputs of build_merkle_circuit for an external witness generator: the 8 blinding values, the 2^(height-1) leaves (both
+// drawn from the witness seed in the generator's order) and the hash parameters (9 MDS row-major, 3 pre-round keys, 63 x 3
+// round constants)
+void zpo_merkle_inputs(int height, uint64_t witness_seed, uint64_t* blinding8, uint64_t* leaves, uint64_t* params201) {
+    ensure_init();
+    SplitMix64 rng(witness_seed);
+    for (int i = 0; i < 8; i++) memcpy(blinding8 + 4 * i, rng.next_fr().v, 32);
+    size_t nleaves = (size_t)1 << (height - 1);
+    for (size_t i = 0; i < nleaves; i++) memcpy(leaves + 4 * i, rng.next_fr().v, 32);
+    HashParams hp(0x504f534549444f4eULL);
+    uint64_t* o = params201;
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++, o += 4) memcpy(o, hp.mds[i][j].v, 32);
+    for (int j = 0; j < 3; j++, o += 4) memcpy(o, hp.ark0[j].v, 32);
+    for (int r = 0; r < 63; r++)
+        for (int j = 0; j < 3; j++, o += 4) memcpy(o, hp.rc[r][j].v, 32);
+}
+
 // every gate equation of the synthetic circuit holds on the witness (sanity of the generator itself): arithmetic + PI
 // + the four custom widgets (separation challenges drawn at random) on every row, "next" = the following row, and
 // every lookup row is in the table

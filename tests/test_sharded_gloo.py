@@ -55,6 +55,16 @@ def _worker(rank, world, port, emu_path, out_dir, n_lookup=0, env=None):
         dist.broadcast(t, src=root)
 
     ctx.set_device_broadcast(bcast)
+
+    def allgather_inplace(ptr, nbytes):
+        import ctypes
+        buf = (ctypes.c_uint8 * (nbytes * world)).from_address(ptr)
+        whole = torch.frombuffer(buf, dtype=torch.uint8)
+        mine = whole[rank * nbytes:(rank + 1) * nbytes].clone()
+        dist.all_gather_into_tensor(whole, mine)
+
+    if os.environ.get("ZP_TEST_ALLGATHER", "1") != "0":
+        ctx.set_device_allgather(allgather_inplace)
     circ = pkg.make_circuit(oc.cs_n, oc.lookup_len, oc.pi_pos, oc.q_lookup(), oc.pi_canonical(), *oc.wires())
     proof = ctx.prove(circ).to_words()
     np.save(os.path.join(out_dir, "proof_%d.npy" % rank), proof)
@@ -71,7 +81,10 @@ BUCKETS = {"ZP_MSM_PRECOMP_MIN_LOG": "8", "ZP_MSM_BA_MIN_LOG": "8", "ZP_MSM_BA_R
 
 
 @pytest.mark.parametrize("world,n_lookup,env", [(2, 0, None), (4, 12, None), (2, 0, BUCKETS), (4, 12, BUCKETS),
-                                                (2, 0, dict(BUCKETS, ZP_SHARD_BUCKETS="0"))])
+                                                (2, 0, dict(BUCKETS, ZP_SHARD_BUCKETS="0", ZP_TEST_ALLGATHER="0")),
+                                                # one coset per rank: compact per-rank copies of the key streams, dealt wire iNTTs
+                                                (8, 12, dict(BUCKETS, ZP_DEAL_MIN_LOG="0")),
+                                                (8, 0, dict(ZP_DEAL_MIN_LOG="0", ZP_COSET_COPIES="0", ZP_TEST_ALLGATHER="0"))])
 def test_sharded_msm_two_ranks(pkg, oracle, tmp_path, world, n_lookup, env):
     import oracle_lib
     emu_path = pkg._build.build_emu()

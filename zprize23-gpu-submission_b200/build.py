@@ -11,7 +11,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["ntt.cu", "msm.cu", "poly.cu", "wiring.cu", "prover.cu", "verifier.cu", "capi.cu"]
+SOURCES = ["ntt.cu", "msm.cu", "poly.cu", "wiring.cu", "witness.cu", "prover.cu", "verifier.cu", "capi.cu"]
 HEADERS = ["ptx_ops.cuh", "field.cuh", "curve.cuh", "common.cuh", "ntt.cuh", "msm.cuh", "msm_affine.cuh", "poly.cuh", "wiring.cuh", "gates.cuh",
            "host_math.hpp", "pairing.hpp", "transcript.hpp", "prover.cuh"]
 LIB = os.path.join(HERE, "libzprize_b200.so")
@@ -47,7 +47,7 @@ def build(verbose=False):
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
         if _newer_than(obj, deps):
             jobs.append([nvcc] + flags + ["-c", os.path.join(CSRC, src), "-o", obj])
-    with ThreadPoolExecutor(max_workers=7) as ex:
+    with ThreadPoolExecutor(max_workers=8) as ex:
         outs = list(ex.map(_run, jobs))
     if verbose:
         for o in outs:
@@ -75,7 +75,7 @@ def build_emu():
         jobs.append([cxx] + flags + ["-x", "c++", "-c", os.path.join(CSRC, src), "-o", obj])
     jobs.append([cxx, "-std=c++17", "-O2", "-fPIC", "-c", os.path.join(EMU_DIR, "cuda_emu.cpp"), "-o",
                  os.path.join(objdir, "cuda_emu.o")])
-    with ThreadPoolExecutor(max_workers=7) as ex:
+    with ThreadPoolExecutor(max_workers=8) as ex:
         list(ex.map(_run, jobs))
     objs = [os.path.join(objdir, s.replace(".cu", ".o")) for s in SOURCES] + [os.path.join(objdir, "cuda_emu.o")]
     _run([cxx, "-shared", "-o", EMU_LIB] + objs)

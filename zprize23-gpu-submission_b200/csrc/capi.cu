@@ -142,6 +142,12 @@ int zp_prover_read_pk(zp_prover* p, int index, uint64_t* coeffs_out, uint64_t* e
 int zp_prover_verifier_key(zp_prover* p, uint64_t* out) { return guard([&] { P(p)->verifier_key(out); }); }
 int zp_prover_prove(zp_prover* p, const CircuitC* c, ProofC* out) { return guard([&] { P(p)->prove(*c, out); }); }
 int zp_prover_upload_witness(zp_prover* p, const CircuitC* c) { return guard([&] { P(p)->upload_witness(*c); }); }
+int zp_prover_synthesize_merkle_witness(zp_prover* p, int height, const uint64_t* leaves, const uint64_t* hash_params,
+                                        const uint64_t* blinding, uint64_t* root_out) {
+    return guard([&] { P(p)->synthesize_merkle_witness(height, leaves, hash_params, blinding, root_out); });
+}
+int zp_prover_read_witness(zp_prover* p, int wire, uint64_t* out) { return guard([&] { P(p)->read_witness(wire, out); }); }
+uint64_t zp_prover_witness_rows(zp_prover* p) { return P(p)->wit_n; }
 int zp_prover_prove_resident(zp_prover* p, ProofC* out) { return guard([&] { P(p)->prove_resident(out); }); }
 int zp_prover_collect_msm_stats(zp_prover* p, int enable) { return guard([&] { P(p)->collect_msm_stats = enable != 0; }); }
 int zp_prover_msm_stats(zp_prover* p, double* out9) {
@@ -172,6 +178,12 @@ int zp_prover_set_device_broadcast(zp_prover* p, zp_dev_broadcast_fn fn, void* u
     return guard([&] {
         P(p)->dev_bcast = fn;
         P(p)->dev_bcast_user = user;
+    });
+}
+int zp_prover_set_device_allgather(zp_prover* p, zp_dev_allgather_fn fn, void* user) {
+    return guard([&] {
+        P(p)->dev_allgather = fn;
+        P(p)->dev_allgather_user = user;
     });
 }
 int zp_prover_last_timing(zp_prover* p, double* out_ms, int n) {

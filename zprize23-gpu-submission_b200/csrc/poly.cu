@@ -494,12 +494,20 @@ __global__ void __launch_bounds__(128) quotient_kernel(QuotientArgs a) {
     t += a.i_begin;
     // i: natural index on the 8N domain (prover-key streams, l1, x, Z_H); wi / nx: index of this point and of the "next"
     // point (omega * x) in the wire-like arrays
-    size_t i = t, wi = t, nx = (t + 8) & (n8 - 1);
+    // ki: index into the prover-key streams and l1 (natural 8N order, or this coset's compact copy); kmask / kshift: the
+    // public-input rotation in that indexing
+    size_t i = t, wi = t, nx = (t + 8) & (n8 - 1), ki = t, kmask = n8 - 1, kshift = a.pi_shift;
     if (a.coset_j >= 0) {
         const size_t nn = n8 >> 3, c = t & (((size_t)1 << a.coset_lc) - 1), tt = t >> a.coset_lc;
         i = 8 * tt + (size_t)a.coset_j + c;
         wi = c * nn + tt;
         nx = c * nn + ((tt + 1) & (nn - 1));
+        ki = i;
+        if (a.compact_key) {
+            ki = tt;
+            kmask = nn - 1;
+            kshift = a.pi_shift >> 3;
+        }
     }
     const fr_t one = fr_t::one();
     GateVals<fr_t> g;
@@ -509,29 +517,29 @@ __global__ void __launch_bounds__(128) quotient_kernel(QuotientArgs a) {
     g.d = load_fr(&a.w[3][wi]);
 
     // ---- arithmetic widget (arithmetic.rs:61-79)
-    fr_t arith = a.sel[5] ? load_fr(&a.sel[5][i]) : fr_t::zero();  // q_c (dropped when identically zero, like every selector)
+    fr_t arith = a.sel[5] ? load_fr(&a.sel[5][ki]) : fr_t::zero();  // q_c (dropped when identically zero, like every selector)
     g.q_c = arith;
-    if (a.sel[0]) arith = arith + g.a * g.b * load_fr(&a.sel[0][i]);
-    g.q_l = a.sel[1] ? load_fr(&a.sel[1][i]) : fr_t::zero();
-    g.q_r = a.sel[2] ? load_fr(&a.sel[2][i]) : fr_t::zero();
+    if (a.sel[0]) arith = arith + g.a * g.b * load_fr(&a.sel[0][ki]);
+    g.q_l = a.sel[1] ? load_fr(&a.sel[1][ki]) : fr_t::zero();
+    g.q_r = a.sel[2] ? load_fr(&a.sel[2][ki]) : fr_t::zero();
     if (a.sel[1]) arith = arith + g.a * g.q_l;
     if (a.sel[2]) arith = arith + g.b * g.q_r;
-    if (a.sel[3]) arith = arith + g.c * load_fr(&a.sel[3][i]);
-    if (a.sel[4]) arith = arith + g.d * load_fr(&a.sel[4][i]);
-    if (a.sel[6]) arith = arith + g.a.pow5() * load_fr(&a.sel[6][i]);
-    if (a.sel[7]) arith = arith + g.b.pow5() * load_fr(&a.sel[7][i]);
-    if (a.sel[8]) arith = arith + g.d.pow5() * load_fr(&a.sel[8][i]);
-    fr_t total = a.sel[9] ? arith * load_fr(&a.sel[9][i]) : fr_t::zero();
-    if (a.pi_count) total = total + a.pi_val * load_fr(&a.l1[(i - a.pi_shift) & (n8 - 1)]);
+    if (a.sel[3]) arith = arith + g.c * load_fr(&a.sel[3][ki]);
+    if (a.sel[4]) arith = arith + g.d * load_fr(&a.sel[4][ki]);
+    if (a.sel[6]) arith = arith + g.a.pow5() * load_fr(&a.sel[6][ki]);
+    if (a.sel[7]) arith = arith + g.b.pow5() * load_fr(&a.sel[7][ki]);
+    if (a.sel[8]) arith = arith + g.d.pow5() * load_fr(&a.sel[8][ki]);
+    fr_t total = a.sel[9] ? arith * load_fr(&a.sel[9][ki]) : fr_t::zero();
+    if (a.pi_count) total = total + a.pi_val * load_fr(&a.l1[(ki - kshift) & kmask]);
 
     if (CUSTOM) {
         g.a_next = load_fr(&a.w[0][nx]);
         g.b_next = load_fr(&a.w[1][nx]);
         g.d_next = load_fr(&a.w[3][nx]);
-        if (a.sel[10]) total = total + load_fr(&a.sel[10][i]) * range_constraints(a.range_sep, g);
-        if (a.sel[11]) total = total + load_fr(&a.sel[11][i]) * logic_constraints(a.logic_sep, g);
-        if (a.sel[12]) total = total + load_fr(&a.sel[12][i]) * fbsm_constraints(a.fixed_sep, g, a.coeff_d);
-        if (a.sel[13]) total = total + load_fr(&a.sel[13][i]) * curve_add_constraints(a.var_sep, g, a.coeff_d);
+        if (a.sel[10]) total = total + load_fr(&a.sel[10][ki]) * range_constraints(a.range_sep, g);
+        if (a.sel[11]) total = total + load_fr(&a.sel[11][ki]) * logic_constraints(a.logic_sep, g);
+        if (a.sel[12]) total = total + load_fr(&a.sel[12][ki]) * fbsm_constraints(a.fixed_sep, g, a.coeff_d);
+        if (a.sel[13]) total = total + load_fr(&a.sel[13][ki]) * curve_add_constraints(a.var_sep, g, a.coeff_d);
     }
 
     // ---- permutation widget (permutation.rs:62-153); x = g * omega_8N^i  (= linear_evaluations[i])
@@ -544,9 +552,9 @@ __global__ void __launch_bounds__(128) quotient_kernel(QuotientArgs a) {
         fr_t ag = g.a + a.gamma, bg = g.b + a.gamma, cg = g.c + a.gamma, dg = g.d + a.gamma;
         fr_t zi = load_fr(&a.z[wi]), zn = load_fr(&a.z[nx]);
         fr_t id = (ag + bx) * (bg + (b8 - bx)) * (cg + (b8 + b4 + bx)) * (dg + (b16 + bx)) * zi;
-        fr_t cp = (ag + a.beta * load_fr(&a.sigma[0][i])) * (bg + a.beta * load_fr(&a.sigma[1][i])) *
-                  (cg + a.beta * load_fr(&a.sigma[2][i])) * (dg + a.beta * load_fr(&a.sigma[3][i])) * zn;
-        fr_t l1a = load_fr(&a.l1[i]) * a.alpha_sq;
+        fr_t cp = (ag + a.beta * load_fr(&a.sigma[0][ki])) * (bg + a.beta * load_fr(&a.sigma[1][ki])) *
+                  (cg + a.beta * load_fr(&a.sigma[2][ki])) * (dg + a.beta * load_fr(&a.sigma[3][ki])) * zn;
+        fr_t l1a = load_fr(&a.l1[ki]) * a.alpha_sq;
         total = total + (id - cp) * a.alpha + (zi - one) * l1a;
     }
 
@@ -559,10 +567,10 @@ __global__ void __launch_bounds__(128) quotient_kernel(QuotientArgs a) {
         fr_t h1i = load_fr(&a.h1[wi]), h1n = load_fr(&a.h1[nx]), h2i = load_fr(&a.h2[wi]);
         fr_t z2i = load_fr(&a.z2[wi]), z2n = load_fr(&a.z2[nx]);
         fr_t la = fr_t::zero();
-        if (a.sel[14]) la = load_fr(&a.sel[14][i]) * (lc4(g.a, g.b, g.c, g.d, a.zeta) - fi) * a.lookup_sep;
+        if (a.sel[14]) la = load_fr(&a.sel[14][ki]) * (lc4(g.a, g.b, g.c, g.d, a.zeta) - fi) * a.lookup_sep;
         fr_t lb = z2i * opd * (a.epsilon + fi) * (eopd + ti + a.delta * tn) * lsep_sq;
         fr_t lcv = z2n * (eopd + h1i + a.delta * h2i) * (eopd + h2i + a.delta * h1n) * lsep_sq;
-        fr_t ld = (z2i - one) * load_fr(&a.l1[i]) * lsep_cu;
+        fr_t ld = (z2i - one) * load_fr(&a.l1[ki]) * lsep_cu;
         total = total + la + lb - lcv + ld;
     }
     store_fr(&a.out[wi], total * a.vh_inv[i & 7]);

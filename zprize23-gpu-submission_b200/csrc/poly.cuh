@@ -80,6 +80,9 @@ struct QuotientArgs {
     // c * N + t ("next" = t + 1 inside the coset); the prover-key streams and l1 stay in natural 8N order and are read at
     // 8 t + coset_j + c, so neighbouring threads (c fastest) read neighbouring elements.  -1: the whole 8N domain, natural order.
     int coset_j, coset_lc;
+    // 1: sel / sigma / l1 are this coset's COMPACT copies indexed by t (one coset per launch, coset_lc = 0); the public-input
+    // rotation of l1 stays inside the coset (L_pos(x_{8 t + j}) = L_1(x_{8 (t - pos) + j}))
+    int compact_key = 0;
 };
 void quotient_evals(const QuotientArgs& a, cudaStream_t st);
 

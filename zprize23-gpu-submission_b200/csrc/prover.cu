@@ -65,6 +65,8 @@ struct Scope {
 Prover::Prover(int logn_) : logn(logn_), n((size_t)1 << logn_), n8((size_t)8 << logn_) {
     const char* pc = getenv("ZP_MSM_PRECOMP");
     if (pc && pc[0] == '0') use_precomp = false;
+    const char* cc = getenv("ZP_COSET_COPIES");
+    if (cc && cc[0] == '0') coset_copies = false;
     const char* sb = getenv("ZP_SHARD_BUCKETS");
     if (sb && sb[0] == '0') shard_buckets = false;
     const char* pm = getenv("ZP_MSM_PRECOMP_MIN_LOG");
@@ -478,6 +480,34 @@ static inline fr_t D(const Fr& a) { return host::to_dev(a); }
 static inline Fr H(const fr_t& a) { return host::to_host(a); }
 static void put_fr(uint64_t* dst, const Fr& a) { memcpy(dst, a.v, 32); }
 
+void Prover::exchange_blocks(void* base, size_t bytes_per_rank) {
+    if (dev_allgather) {
+        if (dev_allgather(dev_allgather_user, base, bytes_per_rank) != 0) throw std::runtime_error("device all-gather failed");
+        return;
+    }
+    for (int r = 0; r < shard_world; r++)
+        if (dev_bcast(dev_bcast_user, (char*)base + (size_t)r * bytes_per_rank, bytes_per_rank, r) != 0)
+            throw std::runtime_error("device broadcast failed");
+}
+
+__global__ void __launch_bounds__(256) stride8_gather_kernel(const fr_t* __restrict__ in, fr_t* __restrict__ out, size_t n, int j) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) store_fr(&out[t], load_fr(&in[8 * t + j]));
+}
+void Prover::ensure_coset_copies() {
+    if (evals_coset_rank == shard_rank) return;
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    for (int i = 0; i < PK_COUNT; i++) {
+        evals_coset[i].release();
+        if (!evals[i].p) continue;
+        evals_coset[i].alloc(n);
+        ZP_LAUNCH(stride8_gather_kernel, dim3(grid), dim3(256), 0, st, evals[i].p, evals_coset[i].p, n, shard_rank);
+    }
+    l1_coset_c.alloc(n);
+    ZP_LAUNCH(stride8_gather_kernel, dim3(grid), dim3(256), 0, st, l1_coset.p, l1_coset_c.p, n, shard_rank);
+    evals_coset_rank = shard_rank;
+}
+
 void Prover::upload_witness(const CircuitC& c) {
     if (c.n > n || c.n == 0) throw std::runtime_error("zp_prover_prove: circuit size does not fit the domain");
     if (c.intended_pi_pos >= n) throw std::runtime_error("zp_prover_prove: intended_pi_pos lies outside the domain");
@@ -493,11 +523,16 @@ void Prover::upload_witness(const CircuitC& c) {
         const size_t lo = std::min(cn, (size_t)shard_rank * chunk), hi = std::min(cn, lo + chunk);
         for (int k = 0; k < 5; k++)
             if (hi > lo) ZP_CUDA(cudaMemcpyAsync(dev[k] + lo, host[k] + 4 * lo, (hi - lo) * sizeof(fr_t), cudaMemcpyHostToDevice, st));
-        for (int r = 0; r < shard_world; r++) {
-            const size_t rlo = std::min(cn, (size_t)r * chunk), rhi = std::min(cn, rlo + chunk);
-            for (int k = 0; k < 5 && rhi > rlo; k++)
-                if (dev_bcast(dev_bcast_user, dev[k] + rlo, (rhi - rlo) * sizeof(fr_t), r) != 0)
-                    throw std::runtime_error("device broadcast of a witness slice failed");
+        if (dev_allgather) {
+            // equal blocks of `chunk` elements (chunk * world <= N; what lies beyond cn is cleared / ignored below)
+            for (int k = 0; k < 5; k++) exchange_blocks(dev[k], chunk * sizeof(fr_t));
+        } else {
+            for (int r = 0; r < shard_world; r++) {
+                const size_t rlo = std::min(cn, (size_t)r * chunk), rhi = std::min(cn, rlo + chunk);
+                for (int k = 0; k < 5 && rhi > rlo; k++)
+                    if (dev_bcast(dev_bcast_user, dev[k] + rlo, (rhi - rlo) * sizeof(fr_t), r) != 0)
+                        throw std::runtime_error("device broadcast of a witness slice failed");
+            }
         }
     } else {
         for (int k = 0; k < 5; k++) ZP_CUDA(cudaMemcpyAsync(dev[k], host[k], cn * sizeof(fr_t), cudaMemcpyHostToDevice, st));
@@ -550,8 +585,20 @@ void Prover::prove_resident(ProofC* out) {
         const fr_t* wp[4];
         CommitmentC* wc[4];
         Fq x[4], y[4]; bool inf[4];
+        // multi-GPU with a device broadcast: the four independent iNTTs are dealt round-robin and broadcast (128 MiB each
+        // over NVLink is cheaper than the transform); otherwise every rank transforms all four
+        static const int deal_min_log = getenv("ZP_DEAL_MIN_LOG") ? atoi(getenv("ZP_DEAL_MIN_LOG")) : 16;
+        const bool deal = shard_world > 1 && dev_bcast != nullptr && logn >= deal_min_log;
         for (int k = 0; k < 4; k++) {
-            { Scope s(timer, CAT_NTT); ntt_run(T, NS, NTT_INV, logn, w_ev[k].p, n, w_poly[k].p, st); }
+            Scope s(timer, CAT_NTT);
+            if (!deal || k % shard_world == shard_rank) ntt_run(T, NS, NTT_INV, logn, w_ev[k].p, n, w_poly[k].p, st);
+        }
+        for (int k = 0; k < 4; k++) {
+            if (deal) {
+                Scope s(timer, CAT_NTT);
+                if (dev_bcast(dev_bcast_user, w_poly[k].p, n * sizeof(fr_t), k % shard_world) != 0)
+                    throw std::runtime_error("device broadcast of a wire polynomial failed");
+            }
             wp[k] = w_poly[k].p;
             wc[k] = &comm[k];
         }
@@ -734,6 +781,14 @@ void Prover::prove_resident(ProofC* out) {
                 qc.i_count = (size_t)cpr * n;
                 qc.coset_j = shard_rank * cpr;
                 qc.coset_lc = ilog2((size_t)cpr);
+                if (cpr == 1 && coset_copies) {
+                    // one coset per rank: read the key streams from this rank's compact copies (built once)
+                    ensure_coset_copies();
+                    for (int i = 0; i < 15; i++) qc.sel[i] = evals_coset[i].p;
+                    for (int k = 0; k < 4; k++) qc.sigma[k] = evals_coset[PK_SIGL + k].p;
+                    qc.l1 = l1_coset_c.p;
+                    qc.compact_key = 1;
+                }
                 Scope s(timer, CAT_QUOT);
                 quotient_evals(qc, st);
             }
@@ -746,9 +801,7 @@ void Prover::prove_resident(ProofC* out) {
                 if (j) ntt_coset_shift(T, pj, pj, n, logn + 3, j, true, st);
             }
             { Scope s(timer, CAT_NTT);
-              for (int r = 0; r < shard_world; r++)
-                  if (dev_bcast(dev_bcast_user, pj8.p + (size_t)r * cpr * n, (size_t)cpr * n * sizeof(fr_t), r) != 0)
-                      throw std::runtime_error("device broadcast of the per-coset quotient coefficients failed");
+              exchange_blocks(pj8.p, (size_t)cpr * n * sizeof(fr_t));
               ntt_combine8(T, pj8.p, t_poly.p, logn, st);
             }
         }

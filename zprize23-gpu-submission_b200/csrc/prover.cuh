@@ -81,6 +81,18 @@ struct Prover {
     void* allgather_user = nullptr;
     zp_dev_broadcast_fn dev_bcast = nullptr;
     void* dev_bcast_user = nullptr;
+    zp_dev_allgather_fn dev_allgather = nullptr;  // in-place all-gather of device memory (one collective instead of G broadcasts)
+    void* dev_allgather_user = nullptr;
+    // rank r's block [r * bytes, (r + 1) * bytes) of `base` goes to every rank: all-gather hook, else G broadcasts
+    void exchange_blocks(void* base, size_t bytes_per_rank);
+    // multi-GPU quotient round with one coset per rank (world = 8): compact copies sel_c[i][t] = evals[i][8 t + rank] of the
+    // prover-key streams, so the fused pass reads N contiguous elements per stream instead of every 8th of 8N (4x DRAM
+    // over-fetch through 128-byte lines)
+    DevBuf<fr_t> evals_coset[PK_COUNT];
+    DevBuf<fr_t> l1_coset_c;
+    int evals_coset_rank = -1;
+    bool coset_copies = true;  // ZP_COSET_COPIES=0: read the natural-order streams at stride 8 instead
+    void ensure_coset_copies();
 
     explicit Prover(int logn_);
     ~Prover();
@@ -97,6 +109,9 @@ struct Prover {
     void finish_pk();
     void verifier_key(uint64_t* out23);
     void upload_witness(const CircuitC& c);
+    void synthesize_merkle_witness(int height, const uint64_t* leaves, const uint64_t* params, const uint64_t* blinding,
+                                   uint64_t* root_out);
+    void read_witness(int k, uint64_t* out);
     void prove_resident(ProofC* out);
     void prove(const CircuitC& c, ProofC* out);
 

@@ -107,6 +107,10 @@ ALLGATHER_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, 
 DEV_BCAST_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int)
 
 
+# int (*zp_dev_allgather_fn)(void* user, void* dev_base, size_t bytes_per_rank)
+DEV_ALLGATHER_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t)
+
+
 # int (*zp_dev_alltoall_fn)(void* user, const void* send_dev, void* recv_dev, size_t bytes_per_peer)
 DEV_A2A_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t)
 
@@ -153,10 +157,14 @@ def load_library(path=None):
         "zp_prover_last_timing": (ci, [vp, dp, ci]),
         "zp_prover_upload_witness": (ci, [vp, ctypes.POINTER(CircuitC)]),
         "zp_prover_prove_resident": (ci, [vp, ctypes.POINTER(ProofC)]),
+        "zp_prover_synthesize_merkle_witness": (ci, [vp, ci, u64p, u64p, u64p, u64p]),
+        "zp_prover_read_witness": (ci, [vp, ci, u64p]),
+        "zp_prover_witness_rows": (ctypes.c_uint64, [vp]),
         "zp_prover_collect_msm_stats": (ci, [vp, ci]),
         "zp_prover_msm_stats": (ci, [vp, dp]),
         "zp_prover_set_shard": (ci, [vp, ci, ci, ALLGATHER_FN, vp]),
         "zp_prover_set_device_broadcast": (ci, [vp, DEV_BCAST_FN, vp]),
+        "zp_prover_set_device_allgather": (ci, [vp, DEV_ALLGATHER_FN, vp]),
         "zp_ntt_host": (ci, [vp, ci, ci, u64p, u64p]),
         "zp_msm_host": (ci, [vp, u64p, cs, u64p]),
         "zp_msm_batch_host": (ci, [vp, u64p, ci, cs, u64p]),
@@ -202,8 +210,8 @@ def load_library(path=None):
 EXPORTED_SYMBOLS = ["gen_proof", "zp_verifier_last_error", "zp_verifier_create", "zp_verifier_destroy", "zp_verifier_set_label", "zp_proof_verify", "zp_proof_verify_batch", "zp_g2_mul_generator", "zp_pairing_product", "zp_gen_proof_invalidate", "zp_proof_serialize", "zp_proof_deserialize", "zp_last_error", "zp_launch_count", "zp_device_available", "zp_prover_create",
                     "zp_prover_destroy", "zp_prover_set_label", "zp_profiler_range", "zp_prover_set_stream", "zp_prover_load_srs", "zp_prover_generate_srs",
                     "zp_prover_read_srs", "zp_prover_load_pk", "zp_prover_preprocess", "zp_prover_read_pk", "zp_prover_preprocess_wiring", "zp_sigma_from_wiring_host", "zp_prover_verifier_key",
-                    "zp_prover_prove", "zp_prover_last_timing", "zp_prover_upload_witness", "zp_prover_prove_resident",
-                    "zp_prover_collect_msm_stats", "zp_prover_msm_stats", "zp_prover_set_shard", "zp_prover_set_device_broadcast", "zp_ntt_host", "zp_ntt_sharded_host", "zp_bench_ntt_sharded", "zp_msm_host", "zp_msm_batch_host", "zp_msm_points_host",
+                    "zp_prover_prove", "zp_prover_last_timing", "zp_prover_upload_witness", "zp_prover_prove_resident", "zp_prover_synthesize_merkle_witness", "zp_prover_read_witness", "zp_prover_witness_rows",
+                    "zp_prover_collect_msm_stats", "zp_prover_msm_stats", "zp_prover_set_shard", "zp_prover_set_device_broadcast", "zp_prover_set_device_allgather", "zp_ntt_host", "zp_ntt_sharded_host", "zp_bench_ntt_sharded", "zp_msm_host", "zp_msm_batch_host", "zp_msm_points_host",
                     "zp_poly_eval_host", "zp_poly_divide_host", "zp_prefix_product_host", "zp_combine_split_host", "zp_multiset_combine_split_host", "zp_multiset_compress_host", "zp_bench_alloc",
                     "zp_bench_upload", "zp_bench_download", "zp_bench_ntt", "zp_bench_ntt_padded", "zp_bench_msm", "zp_bench_msm_batch", "zp_bench_msm_breakdown",
                     "zp_bench_int_pipe"]
@@ -433,6 +441,20 @@ class ProverContext:
     def upload_witness(self, circuit):
         self._ck(self.lib.zp_prover_upload_witness(self.h, ctypes.byref(circuit)))
 
+    def synthesize_merkle_witness(self, height, leaves, hash_params, blinding):
+        """Builds the Poseidon-Merkle witness on the device (resident for prove_resident); returns the root (Montgomery)."""
+        root = np.zeros(4, dtype=np.uint64)
+        self._ck(self.lib.zp_prover_synthesize_merkle_witness(self.h, height, as_u64p(leaves), as_u64p(hash_params),
+                                                              as_u64p(blinding), as_u64p(root)))
+        return root
+
+    def read_witness(self):
+        rows = self.lib.zp_prover_witness_rows(self.h)
+        out = [np.zeros((rows, 4), dtype=np.uint64) for _ in range(4)]
+        for k in range(4):
+            self._ck(self.lib.zp_prover_read_witness(self.h, k, as_u64p(out[k])))
+        return out
+
     def prove_resident(self):
         proof = ProofC()
         self._ck(self.lib.zp_prover_prove_resident(self.h, ctypes.byref(proof)))
@@ -477,6 +499,22 @@ class ProverContext:
                     return 1
             self._bc = DEV_BCAST_FN(_cb)
         self._ck(self.lib.zp_prover_set_device_broadcast(self.h, self._bc, None))
+
+    def set_device_allgather(self, allgather):
+        """allgather(dev_base: int, bytes_per_rank: int): in-place all-gather of device memory — rank r's block
+        [r * bytes_per_rank, (r + 1) * bytes_per_rank) reaches every rank (None disables)."""
+        if allgather is None:
+            self._ag = ctypes.cast(None, DEV_ALLGATHER_FN)
+        else:
+            def _cb(user, ptr, nbytes):
+                try:
+                    allgather(ptr, nbytes)
+                    return 0
+                except Exception as e:  # noqa: BLE001
+                    self._cb_error = e
+                    return 1
+            self._ag = DEV_ALLGATHER_FN(_cb)
+        self._ck(self.lib.zp_prover_set_device_allgather(self.h, self._ag, None))
 
     def last_timing(self):
         out = (ctypes.c_double * 5)()
