@@ -10,12 +10,14 @@
 //                  threads; long buckets are split so no digit distribution serialises
 //   6. reduce    : row / column sums of the bucket matrix, then weight * sum and a tree (msm_rowcol_kernel, msm_weighted_kernel)
 //   host         : with precomputed window tables one XYZZ point per member; otherwise Horner over the window sums; to affine
-// Multi-GPU (precomputed tables only): ranks split the BUCKETS, not the points.  A launch with cfg.bucket_lo / cfg.nbuckets
-// keeps only the digits whose bucket lies in [bucket_lo, bucket_lo + nbuckets) and numbers them locally; every rank walks all
+// Multi-GPU (precomputed tables only): ranks split the BUCKETS, not the points.  A launch with cfg.bucket_lg = log2 G keeps
+// only the digits whose bucket g satisfies g mod G == bucket_rank and numbers them locally j = g / G; every rank walks all
 // scalars (cheap, HBM-bound) but accumulates 1/G of the bucket entries at the SAME window size and bucket load as one GPU
 // (point-range slices force c down — 16 windows instead of 13 at 2^19 points — and starve the batch-affine rounds).  The
-// reduction returns sum (j_local + 1) B_j and the plain sum T of the slice; the true weights are j_local + 1 + bucket_lo, so
-// the rank's share is  weighted + bucket_lo * T  (one short scalar multiplication on the host).
+// split is CYCLIC because the short top window only produces small digits: contiguous ranges would hand all of its
+// entries to rank 0 (+67 % load, measured as a straggler at G = 8).  The reduction returns W = sum (j + 1) B_j and the plain
+// sum T of the rank's buckets; the true weight of local bucket j is j G + bucket_rank + 1, so the rank's share is
+// G W + (bucket_rank + 1 - G) T  (two short scalar multiplications on the host).
 // Order inside a bucket is not deterministic (atomics) but the group sum is exact, so the affine
 // result is bit-identical run to run.
 #include "msm.cuh"
@@ -98,8 +100,8 @@ void MsmWorkspace::reserve(size_t n, const MsmConfig& cfg, int nbatch) {
 }
 
 // blockIdx.y = member of the batch (several scalar vectors over the same points, one bucket-set group each)
-__global__ void __launch_bounds__(256) msm_digits_kernel(MsmBatch batch, size_t n, int c, int nwin, int nbuckets, uint32_t bucket_lo,
-                                                         int one_set, uint32_t* __restrict__ digits, uint32_t* __restrict__ hist) {
+__global__ void __launch_bounds__(256) msm_digits_kernel(MsmBatch batch, size_t n, int c, int nwin, int nbuckets, int bucket_lg,
+                                                         uint32_t bucket_rank, int one_set, uint32_t* __restrict__ digits, uint32_t* __restrict__ hist) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const fr_t* __restrict__ scalars = batch.s[blockIdx.y];
@@ -126,10 +128,10 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(MsmBatch batch, size_t 
         } else {
             carry = 0;
         }
-        // bucket slice of this launch: global bucket d - 1 -> local bucket d - 1 - bucket_lo, digits outside are dropped
-        if (d) {
-            const uint32_t g = d - 1 - bucket_lo;  // wraps below the slice
-            d = g < (uint32_t)nbuckets ? g + 1 : 0;
+        // bucket share of this launch: global bucket g = d - 1 is ours iff g mod 2^bucket_lg == bucket_rank; local index g >> bucket_lg
+        if (d && bucket_lg) {
+            const uint32_t g = d - 1;
+            d = (g & ((1u << bucket_lg) - 1)) == bucket_rank ? (g >> bucket_lg) + 1 : 0;
         }
         digits[(size_t)w * n + i] = d | (neg << 31);
         if (d) atomicAdd(&hist[(one_set ? 0 : (size_t)w * nbuckets) + d - 1], 1u);
@@ -516,7 +518,7 @@ static void msm_launch_impl(MsmWorkspace& ws, const MsmConfig& cfg, const affine
     mark(0);
     if (n) {
         ZP_LAUNCH(msm_digits_kernel, dim3((unsigned)((n + 255) / 256), nbatch), dim3(256), 0, st, batch, n, cfg.c, cfg.nwin,
-                  cfg.nbuckets, cfg.bucket_lo, cfg.tab_stride ? 1 : 0, ws.digits.p, ws.cursor.p);
+                  cfg.nbuckets, cfg.bucket_lg, cfg.bucket_rank, cfg.tab_stride ? 1 : 0, ws.digits.p, ws.cursor.p);
     }
     mark(1);
     msm_scan(ws.cursor.p, ws.start.p, wb, ws.tile_sum.p, st);
@@ -531,7 +533,7 @@ static void msm_launch_impl(MsmWorkspace& ws, const MsmConfig& cfg, const affine
     const affine_t* pts = points;
     uint32_t pstride = cfg.pt_stride;  // the materialised partial sums of the batch-affine rounds are packed affine_t
     size_t est = wn;  // upper bound on the bucket entries still to be added
-    const bool bucket_slice = cfg.nbuckets != (1 << (cfg.c - 1));
+    const bool bucket_slice = cfg.bucket_lg > 0;
     if (bucket_slice) {
         // only the digits of this rank's bucket slice were kept: size the rounds by what is really there (one 4-byte read)
         uint32_t total = 0;
@@ -638,13 +640,13 @@ static void msm_launch_impl(MsmWorkspace& ws, const MsmConfig& cfg, const affine
     ZP_LAUNCH(msm_weighted_kernel, dim3((unsigned)(nsets * groups)), dim3(128), 0, st, ws.rowcol.p, cfg.nbuckets, lw2, groups,
               ws.partial.p);
     ZP_LAUNCH(msm_final_kernel, dim3(nsets), dim3(128), 0, st, ws.partial.p, groups, ws.final_sums.p);
-    if (cfg.bucket_lo) {
-        // plain sum of the slice's buckets = sum of its column sums rc[set][W1 .. W1 + W2)
+    if (cfg.bucket_lg) {
+        // plain sum of the rank's buckets = sum of its column sums rc[set][W1 .. W1 + W2)
         const int W2 = 1 << lw2, W1 = cfg.nbuckets >> lw2;
         ZP_LAUNCH(msm_plain_total_kernel, dim3(nsets), dim3(128), 0, st, ws.rowcol.p, W1, W2, ws.final_sums.p + nsets);
     }
     mark(6);
-    ZP_CUDA(cudaMemcpyAsync(ws.partial_host.data(), ws.final_sums.p, (size_t)(cfg.bucket_lo ? 2 : 1) * nsets * sizeof(xyzz_t),
+    ZP_CUDA(cudaMemcpyAsync(ws.partial_host.data(), ws.final_sums.p, (size_t)(cfg.bucket_lg ? 2 : 1) * nsets * sizeof(xyzz_t),
                             cudaMemcpyDeviceToHost, st));
     if (ws.ba_used) {
         // entries the accumulate kernel saw (for the roofline accounting) + the degenerate-pair flag
@@ -703,14 +705,20 @@ std::vector<host::G1> msm_collect_batch(MsmWorkspace& ws, const MsmConfig& cfg, 
         host::G1 total = host::G1::infinity();
         if (cfg.nsets == 1) {
             total = host::G1::from_dev(ph[0]);  // precomputed tables: window weights are in the points
-            if (cfg.bucket_lo) {
-                // bucket slice: true weight of local bucket j is j + 1 + bucket_lo  =>  add bucket_lo * (plain sum of the slice)
-                host::G1 plain = host::G1::from_dev(ws.partial_host[(size_t)ws.last_nbatch + b]), acc = host::G1::infinity();
-                for (int bit = 31 - __builtin_clz(cfg.bucket_lo); bit >= 0; bit--) {
-                    acc.dbl_inplace();
-                    if ((cfg.bucket_lo >> bit) & 1) acc.add(plain);
+            if (cfg.bucket_lg) {
+                // cyclic bucket share: true weight of local bucket j is j G + rank + 1  =>  G W - (G - 1 - rank) T
+                host::G1 plain = host::G1::from_dev(ws.partial_host[(size_t)ws.last_nbatch + b]);
+                for (int k = 0; k < cfg.bucket_lg; k++) total.dbl_inplace();
+                const uint32_t m = (1u << cfg.bucket_lg) - 1 - cfg.bucket_rank;
+                if (m) {
+                    host::G1 acc = host::G1::infinity();
+                    for (int bit = 31 - __builtin_clz(m); bit >= 0; bit--) {
+                        acc.dbl_inplace();
+                        if ((m >> bit) & 1) acc.add(plain);
+                    }
+                    acc.Y = acc.Y.neg();
+                    total.add(acc);
                 }
-                total.add(acc);
             }
         } else {
             for (int w = cfg.nwin - 1; w >= 0; w--) {

@@ -12,7 +12,10 @@ struct MsmConfig {
     int c;              // window bits
     int nwin;           // number of windows = ceil(256 / c)
     int nbuckets;       // buckets per bucket set accumulated by this launch: 2^(c-1), or a power-of-two slice of them
-    uint32_t bucket_lo = 0;  // first global bucket of that slice (multi-GPU sharding by BUCKET range, see msm.cu); 0 = all
+    // multi-GPU sharding by BUCKETS (see msm.cu): this launch owns the global buckets g with g mod 2^bucket_lg == bucket_rank,
+    // numbered locally g >> bucket_lg; nbuckets = 2^(c-1) >> bucket_lg.  bucket_lg = 0: all buckets.
+    int bucket_lg = 0;
+    uint32_t bucket_rank = 0;
     int nsets;          // bucket sets: nwin normally, 1 with precomputed window tables
     size_t tab_stride;  // 0, or the row stride of a precomputed table [w][i] = 2^(c w) * P_i
     uint32_t pt_stride; // bytes between consecutive points: 96 (FFI affine_t) or 128 (padded table entries)

@@ -368,6 +368,11 @@ bool Prover::shard_by_buckets(size_t ncoef) const {
 std::vector<host::G1> Prover::msm_over_srs_batch(const fr_t* const* scalars_dev, int k, size_t lo, size_t hi, size_t slice,
                                                  int bucket_rank, int bucket_world) {
     MsmConfig cfg = msm_config_for(hi - lo);
+    // measurement knob: time one rank's share of a bucket-sharded MSM on a single GPU (tools/bench_msm.py)
+    if (bucket_world == 1 && getenv("ZP_BENCH_BUCKET_WORLD")) {
+        bucket_world = atoi(getenv("ZP_BENCH_BUCKET_WORLD"));
+        bucket_rank = getenv("ZP_BENCH_BUCKET_RANK") ? atoi(getenv("ZP_BENCH_BUCKET_RANK")) : bucket_world - 1;
+    }
     const affine_t* base = srs.p + lo;
     if (use_precomp && hi - lo >= precomp_min) {
         if (!(srs_tab.p && tab_lo == lo && tab_n >= hi - lo)) {
@@ -381,8 +386,9 @@ std::vector<host::G1> Prover::msm_over_srs_batch(const fr_t* const* scalars_dev,
         cfg = tab_cfg;
         base = reinterpret_cast<const affine_t*>(srs_tab.p);
         if (bucket_world > 1) {
-            cfg.nbuckets = tab_cfg.nbuckets / bucket_world;
-            cfg.bucket_lo = (uint32_t)bucket_rank * (uint32_t)cfg.nbuckets;
+            cfg.bucket_lg = ilog2((size_t)bucket_world);
+            cfg.bucket_rank = (uint32_t)bucket_rank;
+            cfg.nbuckets = tab_cfg.nbuckets >> cfg.bucket_lg;
         }
     } else if (bucket_world > 1) {
         throw std::runtime_error("msm: bucket sharding needs the precomputed-table route");
