@@ -297,6 +297,10 @@ int zp_bench_msm(zp_prover* p, int slot, size_t n, int iters, double* ms, uint64
 /* the same for `nbatch` (<= 8) scalar vectors over the same points in ONE pipeline (the batch the prover uses for
  * independent commitments); *ms = average device ms per batch */
 int zp_bench_msm_batch(zp_prover* p, int slot, size_t n, int nbatch, int iters, double* ms, uint64_t* out_affine);
+/* the same through the prover's commitment path, which honours zp_prover_set_shard: every rank calls it with the same scalars
+ * (one process per GPU), the MSM is split across the ranks (bucket shares with precomputed tables, point ranges below
+ * 2^16) and the partial sums are all-gathered; *ms = average device ms per batch on this rank, out_affine = the full sum */
+int zp_bench_commit_sharded(zp_prover* p, int slot, size_t n, int nbatch, int iters, double* ms, uint64_t* out_affine);
 /* per-stage device time of the last zp_bench_msm iteration: digits, scan, scatter, batch-affine rounds,
  * accumulate (+ folds), reduce */
 int zp_bench_msm_breakdown(zp_prover* p, double* ms6);

@@ -16,7 +16,8 @@ def ctx(pkg, emu_lib):
     c.close()
 
 
-@pytest.mark.parametrize("logn", [1, 5, 9, 10, 12])
+# 12 .. 18: passes of 6, 7, 8 and 9 stages run in the register-resident radix-8 kernel (ntt_pass8_kernel)
+@pytest.mark.parametrize("logn", [1, 5, 9, 10, 12, 13, 15, 16, 18])
 def test_ntt_family(ctx, oracle, logn):
     x = oracle.random_fr(1, 1 << logn)
     for kind in range(4):

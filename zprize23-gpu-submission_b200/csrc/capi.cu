@@ -719,6 +719,37 @@ int zp_bench_msm_batch(zp_prover* p, int slot, size_t n, int nbatch, int iters, 
         cudaEventDestroy(e1);
     });
 }
+int zp_bench_commit_sharded(zp_prover* p, int slot, size_t n, int nbatch, int iters, double* ms, uint64_t* out_affine) {
+    return guard([&] {
+        if (nbatch < 1 || nbatch > MSM_MAX_BATCH) throw std::runtime_error("zp_bench_commit_sharded: batch size out of range");
+        Prover* pr = P(p);
+        BenchState& b = bench_of(p);
+        if (b.slot[slot].n < n || pr->srs.n < n) throw std::runtime_error("zp_bench_commit_sharded: slot or SRS too small");
+        const fr_t* sp[MSM_MAX_BATCH];
+        CommitmentC cm[MSM_MAX_BATCH];
+        CommitmentC* cp[MSM_MAX_BATCH];
+        host::Fq xs[MSM_MAX_BATCH], ys[MSM_MAX_BATCH];
+        bool infs[MSM_MAX_BATCH];
+        for (int k = 0; k < nbatch; k++) {
+            sp[k] = b.slot[slot].p;
+            cp[k] = &cm[k];
+        }
+        pr->commit_batch(sp, nbatch, n, cp, xs, ys, infs);  // warm-up: tables, workspace
+        cudaEvent_t e0, e1;
+        ZP_CUDA(cudaEventCreate(&e0));
+        ZP_CUDA(cudaEventCreate(&e1));
+        ZP_CUDA(cudaEventRecord(e0, pr->st));
+        for (int i = 0; i < iters; i++) pr->commit_batch(sp, nbatch, n, cp, xs, ys, infs);
+        ZP_CUDA(cudaEventRecord(e1, pr->st));
+        ZP_CUDA(cudaEventSynchronize(e1));
+        float t = 0;
+        ZP_CUDA(cudaEventElapsedTime(&t, e0, e1));
+        *ms = t / iters;
+        if (out_affine) memcpy(out_affine, &cm[0], sizeof(CommitmentC));
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    });
+}
 int zp_bench_msm_breakdown(zp_prover* p, double* ms6) {
     return guard([&] {
         for (int k = 0; k < 6; k++) ms6[k] = bench_of(p).msm_ms[k];

@@ -571,8 +571,27 @@ static void msm_launch_impl(MsmWorkspace& ws, const MsmConfig& cfg, const affine
             msm_scan(ws.ba_cnt.p, rs, wb, ws.tile_sum.p, st);
             ZP_LAUNCH(ba_slots_kernel, dim3((unsigned)((wb * 32 + 255) / 256)), dim3(256), 0, st, run_begin, run_end, rs, wb,
                       ws.ba_src.p);
-            ZP_LAUNCH(ba_up0_kernel, dim3(nblk), dim3(BA_T), 0, st, ws.ba_src.p, rs + wb, cap, entries, pts, pstride, ws.ba_pre.p,
-                      ws.ba_den.p, ws.ba_flag.p);
+            static const int ba_pf = getenv("ZP_BA_PF") ? atoi(getenv("ZP_BA_PF")) : 0;
+            static const int ba_ng = getenv("ZP_BA_NG") ? atoi(getenv("ZP_BA_NG")) : 1;
+            if (ba_ng == 2) {
+                auto k = ba_up0_ng_kernel<2>;
+                ZP_LAUNCH(k, dim3((nblk + 1) / 2), dim3(BA_T), 0, st, ws.ba_src.p, rs + wb, cap, entries, pts, pstride, ws.ba_pre.p, ws.ba_den.p, ws.ba_flag.p, nblk);
+            } else if (ba_ng == 4) {
+                auto k = ba_up0_ng_kernel<4>;
+                ZP_LAUNCH(k, dim3((nblk + 3) / 4), dim3(BA_T), 0, st, ws.ba_src.p, rs + wb, cap, entries, pts, pstride, ws.ba_pre.p, ws.ba_den.p, ws.ba_flag.p, nblk);
+            } else if (ba_pf == 1) {
+                auto k = ba_up0_pf_kernel<1>;
+                ZP_LAUNCH(k, dim3(nblk), dim3(BA_T), 0, st, ws.ba_src.p, rs + wb, cap, entries, pts, pstride, ws.ba_pre.p, ws.ba_den.p, ws.ba_flag.p);
+            } else if (ba_pf == 2) {
+                auto k = ba_up0_pf_kernel<2>;
+                ZP_LAUNCH(k, dim3(nblk), dim3(BA_T), 0, st, ws.ba_src.p, rs + wb, cap, entries, pts, pstride, ws.ba_pre.p, ws.ba_den.p, ws.ba_flag.p);
+            } else if (ba_pf == 4) {
+                auto k = ba_up0_pf_kernel<4>;
+                ZP_LAUNCH(k, dim3(nblk), dim3(BA_T), 0, st, ws.ba_src.p, rs + wb, cap, entries, pts, pstride, ws.ba_pre.p, ws.ba_den.p, ws.ba_flag.p);
+            } else {
+                ZP_LAUNCH(ba_up0_kernel, dim3(nblk), dim3(BA_T), 0, st, ws.ba_src.p, rs + wb, cap, entries, pts, pstride, ws.ba_pre.p,
+                          ws.ba_den.p, ws.ba_flag.p);
+            }
             fq_batch_inverse(ws.ba_den.p, m, ws.ba_den.p + m, st);
             if (stats) {
                 if (!ws.down_ev[2 * r]) {

@@ -77,6 +77,144 @@ __global__ void __launch_bounds__(BA_T) ba_up0_kernel(const uint32_t* __restrict
     store_fq(&up[(size_t)blockIdx.x * BA_T + threadIdx.x], acc);
 }
 
+
+// EXPERIMENT (ZP_BA_NG = 2 | 4): NG leaf groups per thread walked in lock step, i.e. NG independent gather -> product chains
+// in flight per thread instead of one (same outputs, same layout as ba_up0_kernel).
+template <int NG>
+__global__ void __launch_bounds__(BA_T) ba_up0_ng_kernel(const uint32_t* __restrict__ src0, const uint32_t* __restrict__ total_ptr,
+                                                         size_t cap, const uint32_t* __restrict__ entries,
+                                                         const affine_t* __restrict__ pts, uint32_t pstride,
+                                                         fq_t* __restrict__ pre, fq_t* __restrict__ up, uint32_t* __restrict__ flag,
+                                                         unsigned ngroups) {
+    const size_t total = *total_ptr;
+    fq_t acc[NG];
+    size_t base[NG];
+    bool live[NG];
+#pragma unroll
+    for (int g = 0; g < NG; g++) {
+        const unsigned grp = blockIdx.x * NG + g;
+        live[g] = grp < ngroups;
+        base[g] = (size_t)grp * (BA_K * BA_T) + threadIdx.x;
+        acc[g] = fq_t::one();
+    }
+#pragma unroll 1
+    for (int k = 0; k < BA_K; k++) {
+        fq_t d[NG];
+        bool pair[NG];
+#pragma unroll
+        for (int g = 0; g < NG; g++) {
+            const size_t j = base[g] + (size_t)k * BA_T;
+            pair[g] = false;
+            if (live[g] && j < cap && j < total) {
+                const uint32_t s = src0[j];
+                if (s & 1u) {
+                    const uint32_t i0 = s >> 1;
+                    const uint32_t e0 = entries ? entries[i0] & 0x7fffffffu : i0, e1 = entries ? entries[i0 + 1] & 0x7fffffffu : i0 + 1;
+                    d[g] = load_fq(&point_at(pts, e1, pstride)->x) - load_fq(&point_at(pts, e0, pstride)->x);
+                    pair[g] = true;
+                }
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < NG; g++) {
+            const size_t j = base[g] + (size_t)k * BA_T;
+            if (!live[g] || j >= cap) continue;
+            if (pair[g] && d[g].is_zero()) {
+                *flag = 1;
+                pair[g] = false;
+            }
+            if (!pair[g]) d[g] = fq_t::one();
+            if (k) store_fq(&pre[j], acc[g]);
+            if (k == 0) acc[g] = d[g];
+            else if (pair[g]) acc[g] = acc[g] * d[g];
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < NG; g++)
+        if (live[g]) store_fq(&up[(size_t)(blockIdx.x * NG + g) * BA_T + threadIdx.x], acc[g]);
+}
+
+ZP_D void prefetch_l2(const void* p) {
+#ifndef ZP_EMU
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+
+// EXPERIMENT (ZP_BA_PF = 1 | 2 | 4, default off): the x-coordinate gathers are random 128-byte lines out of a multi-GiB
+// table; with one dependent gather per loop iteration the kernel above runs at 45 % of DRAM bandwidth (ncu, round 1).
+// This variant walks a thread's slots in chunks of BA_PF: the indices of the NEXT chunk are resolved and their lines
+// requested with prefetch.global.L2 (no registers held) while the current chunk's lines are consumed.  Measured SLOWER at
+// every distance (profiles/r02i_msm_up0_prefetch.log): the prefetched footprint of all resident threads approaches the L2.
+template <int BA_PF>
+__global__ void __launch_bounds__(BA_T) ba_up0_pf_kernel(const uint32_t* __restrict__ src0, const uint32_t* __restrict__ total_ptr,
+                                                      size_t cap, const uint32_t* __restrict__ entries,
+                                                      const affine_t* __restrict__ pts, uint32_t pstride,
+                                                      fq_t* __restrict__ pre, fq_t* __restrict__ up,
+                                                      uint32_t* __restrict__ flag) {
+    const size_t base = (size_t)blockIdx.x * (BA_K * BA_T) + threadIdx.x;
+    const size_t total = *total_ptr;
+    fq_t acc = fq_t::one();
+    uint32_t ea[BA_PF], eb[BA_PF], na[BA_PF], nb[BA_PF];
+    uint32_t pair_cur = 0, pair_next = 0;  // bit i: slot i of the chunk is a real pair
+    auto resolve = [&](int chunk, uint32_t* a, uint32_t* b) -> uint32_t {
+        uint32_t mask = 0;
+#pragma unroll
+        for (int i = 0; i < BA_PF; i++) {
+            const size_t j = base + (size_t)(chunk * BA_PF + i) * BA_T;
+            a[i] = b[i] = 0;
+            if (j < cap && j < total) {
+                const uint32_t s = src0[j];
+                if (s & 1u) {
+                    const uint32_t i0 = s >> 1;
+                    a[i] = entries ? entries[i0] & 0x7fffffffu : i0;
+                    b[i] = entries ? entries[i0 + 1] & 0x7fffffffu : i0 + 1;
+                    mask |= 1u << i;
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < BA_PF; i++)
+            if ((mask >> i) & 1u) {
+                prefetch_l2(&point_at(pts, a[i], pstride)->x);
+                prefetch_l2(&point_at(pts, b[i], pstride)->x);
+            }
+        return mask;
+    };
+    pair_cur = resolve(0, ea, eb);
+#pragma unroll 1
+    for (int chunk = 0; chunk < BA_K / BA_PF; chunk++) {
+        if (chunk + 1 < BA_K / BA_PF) pair_next = resolve(chunk + 1, na, nb);
+#pragma unroll
+        for (int i = 0; i < BA_PF; i++) {
+            const int k = chunk * BA_PF + i;
+            const size_t j = base + (size_t)k * BA_T;
+            if (j >= cap) break;
+            bool pair = (pair_cur >> i) & 1u;
+            fq_t d;
+            if (pair) {
+                d = load_fq(&point_at(pts, eb[i], pstride)->x) - load_fq(&point_at(pts, ea[i], pstride)->x);
+                if (d.is_zero()) {
+                    *flag = 1;
+                    pair = false;
+                }
+            }
+            if (!pair) d = fq_t::one();
+            if (k) store_fq(&pre[j], acc);
+            if (k == 0) acc = d;
+            else if (pair) acc = acc * d;
+        }
+#pragma unroll
+        for (int i = 0; i < BA_PF; i++) {
+            ea[i] = na[i];
+            eb[i] = nb[i];
+        }
+        pair_cur = pair_next;
+    }
+    store_fq(&up[(size_t)blockIdx.x * BA_T + threadIdx.x], acc);
+}
+
 // Leaf level downwards fused with the additions: from inv = 1 / (product of the group) recover each 1 / den[j]
 // (2 products per slot with the stored prefix products) and emit out[j] = P(i0) + P(i0 + 1), or the leftover point.
 __global__ void __launch_bounds__(BA_T, 2) ba_down0_kernel(const uint32_t* __restrict__ src0, const uint32_t* __restrict__ total_ptr,

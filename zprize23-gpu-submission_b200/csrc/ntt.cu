@@ -195,6 +195,170 @@ __global__ void __launch_bounds__(1024) ntt_pass_kernel(const fr_t* __restrict__
     }
 }
 
+// ---- register-resident variant of the pass kernel (lr >= 6, 1024-element tile, 128 threads x 8 elements) -----------
+// The lr radix-2 DIF stages of a tile are grouped 3 + 3 + (lr - 6): in every group a thread holds the 8 elements that
+// differ in the group's three row bits and runs the three stages in REGISTERS (radix-8 butterfly network, 7 twiddle
+// loads), so a tile needs 3 shared-memory exchanges and 3 barriers instead of lr (<= 9) of each; the first group is fused
+// with the global load (coset power / zero padding / inter-pass twiddle applied in flight), the last group's twiddles are
+// the constants w_8^j.  Rows are padded by one row per eight ((row + row / 8) * C + c) so that all three access patterns
+// hit distinct banks.  Same arithmetic, same operand order as ntt_pass_kernel: results are bit-identical.
+ZP_D int pad_idx(int row, int c, int lc) { return ((row + (row >> 3)) << lc) + c; }
+
+// x[i1] = (x[i0] - x[i1]) * w^ex, x[i0] += x[i1]  with the twiddle omega_{2^LMAX}^(+-ex) looked up unless ex == 0
+ZP_D void bfly(fr_t& a, fr_t& b, uint32_t ex, const NttPassParams& p) {
+    fr_t u = a, v = b;
+    a = u + v;
+    fr_t d = u - v;
+    if (ex) {
+        if (p.inverse) ex = ((1u << NTT_LMAX) - ex) & ((1u << NTT_LMAX) - 1);
+        d = d * tw_lookup(p.w_lo, p.w_hi, ex);
+    }
+    b = d;
+}
+// three DIF stages on x[0..8) for the row bits (hi, mid, lo) = register index bits (2, 1, 0); j0 = the part of the in-tile
+// index below the group's bits, unit = weight of the group's lowest bit, s0 = index of the group's first stage
+ZP_D void dif3(fr_t x[8], uint32_t j0, uint32_t unit, int s0, int sh, const NttPassParams& p) {
+#pragma unroll
+    for (int a = 0; a < 4; a++) bfly(x[a], x[a + 4], ((a * unit + j0) << s0) << sh, p);
+#pragma unroll
+    for (int a = 0; a < 2; a++) {
+        const uint32_t ex = ((a * unit + j0) << (s0 + 1)) << sh;
+        bfly(x[a], x[a + 2], ex, p);
+        bfly(x[a + 4], x[a + 6], ex, p);
+    }
+    {
+        const uint32_t ex = (j0 << (s0 + 2)) << sh;
+#pragma unroll
+        for (int a = 0; a < 8; a += 2) bfly(x[a], x[a + 1], ex, p);
+    }
+}
+
+// one DIF stage over register pairs (e, e + HALF); twiddle exponent ((e mod HALF) << s) << sh (compile-time register indices)
+template <int HALF>
+ZP_D void dif_stage_regs(fr_t x[8], int s, int sh, const NttPassParams& p) {
+#pragma unroll
+    for (int e = 0; e < 8; e++)
+        if (!(e & HALF)) bfly(x[e], x[e + HALF], (((uint32_t)e & (HALF - 1)) << s) << sh, p);
+}
+
+__global__ void __launch_bounds__(128) ntt_pass8_kernel(const fr_t* __restrict__ in, fr_t* __restrict__ out, NttPassParams p) {
+    ZP_DYN_SMEM(uint4, sm);
+    const int R = 1 << p.lr, C = 1 << p.lc, RC = R * C;  // RC == 1024
+    const int RCp = (R + (R >> 3)) * C;                   // padded element count
+    const int tid = threadIdx.x;
+    const size_t q0 = (size_t)blockIdx.x << p.lc;
+    const int sh = NTT_LMAX - p.lr;
+    const int c = tid & (C - 1);
+    fr_t x[8];
+
+    // ---- group 1 (row bits lr-1 .. lr-3) fused with the load: thread (rho, c) holds rows a * R/8 + rho
+    {
+        const int rho = tid >> p.lc;
+        const size_t q = q0 + c;
+#pragma unroll
+        for (int a = 0; a < 8; a++) {
+            const int n = a * (R >> 3) + rho;
+            const size_t pos = ((size_t)n << (p.logn - p.lr)) + q;
+            fr_t v;
+            if (p.first) {
+                const bool nz = pos < p.n_in;
+                v = nz ? load_fr(&in[pos]) : fr_t::zero();
+                if (nz && p.coset == 1 && pos != 0) {
+                    uint32_t lo = (uint32_t)pos & ((1u << NTT_LO_BITS) - 1), hi = (uint32_t)(pos >> NTT_LO_BITS);
+                    fr_t f = load_fr(&p.c_lo[lo]);
+                    if (hi) f = f * load_fr(&p.c_hi[hi]);
+                    v = v * f;
+                }
+            } else {
+                v = load_fr(&in[pos]);
+                uint32_t ks = (uint32_t)q & ((1u << p.lk) - 1);
+                uint32_t ex = ((uint32_t)n * ks) << (NTT_LMAX - (p.lk + p.lr));
+                if (ex) {
+                    if (p.tw) {
+                        v = v * load_fr(&p.tw[((size_t)n << p.lk) | ks]);
+                    } else {
+                        if (p.inverse) ex = ((1u << NTT_LMAX) - ex) & ((1u << NTT_LMAX) - 1);
+                        v = v * tw_lookup(p.w_lo, p.w_hi, ex);
+                    }
+                }
+            }
+            x[a] = v;
+        }
+        dif3(x, (uint32_t)rho, (uint32_t)(R >> 3), 0, sh, p);
+#pragma unroll
+        for (int a = 0; a < 8; a++) sm_store(sm, RCp, pad_idx(a * (R >> 3) + rho, c, p.lc), x[a]);
+    }
+    __syncthreads();
+
+    // ---- group 2 (row bits lr-4 .. lr-6): thread (a, r, c) holds rows a * R/8 + b * R/64 + r
+    {
+        const int u = tid >> p.lc;  // (a, r)
+        const int r = u & ((R >> 6) - 1), a = u >> (p.lr - 6);
+        const int row0 = a * (R >> 3) + r;
+#pragma unroll
+        for (int b = 0; b < 8; b++) x[b] = sm_load(sm, RCp, pad_idx(row0 + b * (R >> 6), c, p.lc));
+        dif3(x, (uint32_t)r, (uint32_t)(R >> 6), 3, sh, p);
+#pragma unroll
+        for (int b = 0; b < 8; b++) sm_store(sm, RCp, pad_idx(row0 + b * (R >> 6), c, p.lc), x[b]);
+    }
+    __syncthreads();
+
+    // ---- group 3 (the lr - 6 lowest row bits): thread (u, c) holds rows 8 u .. 8 u + 7; twiddles are w_8^j / w_4^j
+    const int m = p.lr - 6;
+    if (m > 0) {
+        const int u = tid >> p.lc;
+#pragma unroll
+        for (int e = 0; e < 8; e++) x[e] = sm_load(sm, RCp, pad_idx(8 * u + e, c, p.lc));
+        if (m == 3) {
+            dif_stage_regs<4>(x, 6, sh, p);
+            dif_stage_regs<2>(x, 7, sh, p);
+            dif_stage_regs<1>(x, 8, sh, p);
+        } else if (m == 2) {
+            dif_stage_regs<2>(x, 6, sh, p);
+            dif_stage_regs<1>(x, 7, sh, p);
+        } else {
+            dif_stage_regs<1>(x, 6, sh, p);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; e++) sm_store(sm, RCp, pad_idx(8 * u + e, c, p.lc), x[e]);
+        __syncthreads();
+    }
+
+    // ---- store: X[k] sits at the bit-reversed row (identical to ntt_pass_kernel)
+    const int shb = 32 - p.lr;
+    for (int e = tid; e < RC; e += 128) {
+        int k, cc;
+        size_t pos;
+        if (p.first) {
+            k = e & (R - 1);
+            cc = e >> p.lr;
+            pos = (q0 << p.lr) + e;
+        } else {
+            k = e >> p.lc;
+            cc = e & (C - 1);
+            size_t q = q0 + cc;
+            size_t rest = q >> p.lk, ks = q & (((size_t)1 << p.lk) - 1);
+            pos = (rest << (p.lk + p.lr)) + ((size_t)k << p.lk) + ks;
+        }
+        int row = (int)(__brev((uint32_t)k) >> shb);
+        fr_t v = sm_load(sm, RCp, pad_idx(row, cc, p.lc));
+        if (p.last) {
+            if (p.coset == 2 && p.out_tw) {
+                v = v * load_fr(&p.out_tw[pos]);
+            } else if (p.coset == 2) {
+                uint32_t lo = (uint32_t)pos & ((1u << NTT_LO_BITS) - 1), hi = (uint32_t)(pos >> NTT_LO_BITS);
+                fr_t f = p.ninv;
+                if (lo) f = f * load_fr(&p.c_lo[lo]);
+                if (hi) f = f * load_fr(&p.c_hi[hi]);
+                v = v * f;
+            } else if (p.inverse) {
+                v = v * p.ninv;
+            }
+        }
+        store_fr(&out[pos], v);
+    }
+}
+
 // tw[(n << lk) | ks] = omega_{2^(lk+lr)}^{+- n * ks}
 __global__ void ntt_pass_table_kernel(fr_t* __restrict__ tw, int lr, int lk, int inverse, const fr_t* __restrict__ w_lo,
                                       const fr_t* __restrict__ w_hi) {
@@ -315,7 +479,21 @@ void ntt_run(const NttTables& T, NttScratch& S, NttKind kind, int logn, const fr
             attr_set = true;
         }
 #endif
-        ZP_LAUNCH(ntt_pass_kernel, dim3(grid), dim3(threads), smem, st, src, dst, pp);
+        static const bool use_reg = !(getenv("ZP_NTT_REG") && getenv("ZP_NTT_REG")[0] == '0');
+        if (use_reg && pp.lr >= 6 && RC == 1024 && threads == 128) {
+#ifndef ZP_EMU
+            static bool attr8_set = false;
+            if (!attr8_set) {
+                ZP_CUDA(cudaFuncSetAttribute(ntt_pass8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+                ZP_CUDA(cudaFuncSetAttribute(ntt_pass8_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+                attr8_set = true;
+            }
+#endif
+            const size_t smem8 = (size_t)((1 << pp.lr) + (1 << (pp.lr - 3))) * (1 << pp.lc) * 32;
+            ZP_LAUNCH(ntt_pass8_kernel, dim3(grid), dim3(128), smem8, st, src, dst, pp);
+        } else {
+            ZP_LAUNCH(ntt_pass_kernel, dim3(grid), dim3(threads), smem, st, src, dst, pp);
+        }
         if (last && dst != out) ZP_CUDA(cudaMemcpyAsync(out, dst, N * sizeof(fr_t), cudaMemcpyDeviceToDevice, st));
         src = dst;
         lk += bits[p];

@@ -184,6 +184,7 @@ def load_library(path=None):
         "zp_bench_ntt_padded": (ci, [vp, ci, ci, cs, ci, ci, ci, dp]),
         "zp_bench_msm": (ci, [vp, ci, cs, ci, dp, u64p]),
         "zp_bench_msm_batch": (ci, [vp, ci, cs, ci, ci, dp, u64p]),
+        "zp_bench_commit_sharded": (ci, [vp, ci, cs, ci, ci, dp, u64p]),
         "zp_bench_msm_breakdown": (ci, [vp, dp]),
         "zp_bench_int_pipe": (ci, [vp, ci, dp]),
         "zp_proof_serialize": (ci, [ctypes.POINTER(ProofC), ctypes.c_char_p, cs, ctypes.POINTER(cs)]),
@@ -213,7 +214,7 @@ EXPORTED_SYMBOLS = ["gen_proof", "zp_verifier_last_error", "zp_verifier_create",
                     "zp_prover_prove", "zp_prover_last_timing", "zp_prover_upload_witness", "zp_prover_prove_resident", "zp_prover_synthesize_merkle_witness", "zp_prover_read_witness", "zp_prover_witness_rows",
                     "zp_prover_collect_msm_stats", "zp_prover_msm_stats", "zp_prover_set_shard", "zp_prover_set_device_broadcast", "zp_prover_set_device_allgather", "zp_ntt_host", "zp_ntt_sharded_host", "zp_bench_ntt_sharded", "zp_msm_host", "zp_msm_batch_host", "zp_msm_points_host",
                     "zp_poly_eval_host", "zp_poly_divide_host", "zp_prefix_product_host", "zp_combine_split_host", "zp_multiset_combine_split_host", "zp_multiset_compress_host", "zp_bench_alloc",
-                    "zp_bench_upload", "zp_bench_download", "zp_bench_ntt", "zp_bench_ntt_padded", "zp_bench_msm", "zp_bench_msm_batch", "zp_bench_msm_breakdown",
+                    "zp_bench_upload", "zp_bench_download", "zp_bench_ntt", "zp_bench_ntt_padded", "zp_bench_msm", "zp_bench_msm_batch", "zp_bench_commit_sharded", "zp_bench_msm_breakdown",
                     "zp_bench_int_pipe"]
 
 
@@ -630,6 +631,12 @@ class ProverContext:
         bd = (ctypes.c_double * 6)()
         self._ck(self.lib.zp_bench_msm_breakdown(self.h, bd))
         return ms.value, out, dict(zip(["digits", "scan", "scatter", "batch_affine", "accumulate", "reduce"], list(bd)))
+
+    def bench_commit_sharded(self, slot, n, iters, nbatch=1):
+        ms = ctypes.c_double()
+        out = np.zeros(12, dtype=np.uint64)
+        self._ck(self.lib.zp_bench_commit_sharded(self.h, slot, n, nbatch, iters, ctypes.byref(ms), as_u64p(out)))
+        return ms.value, out
 
     def bench_int_pipe(self, mode):
         g = ctypes.c_double()
