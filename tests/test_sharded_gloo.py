@@ -80,11 +80,18 @@ import pytest  # noqa: E402
 BUCKETS = {"ZP_MSM_PRECOMP_MIN_LOG": "8", "ZP_MSM_BA_MIN_LOG": "8", "ZP_MSM_BA_ROUNDS": "2"}
 
 
-@pytest.mark.parametrize("world,n_lookup,env", [(2, 0, None), (4, 12, None), (2, 0, BUCKETS), (4, 12, BUCKETS),
-                                                (2, 0, dict(BUCKETS, ZP_SHARD_BUCKETS="0", ZP_TEST_ALLGATHER="0")),
-                                                # one coset per rank: compact per-rank copies of the key streams, dealt wire iNTTs
-                                                (8, 12, dict(BUCKETS, ZP_DEAL_MIN_LOG="0")),
-                                                (8, 0, dict(ZP_DEAL_MIN_LOG="0", ZP_COSET_COPIES="0", ZP_TEST_ALLGATHER="0"))])
+# the last three repeat a covered mechanism in another mode (point-range MSM shards, no compact coset copies, broadcast
+# instead of all-gather): run with ZP_SLOW_TESTS=1; the default set keeps the CPU suite at a few minutes
+_slow = pytest.mark.skipif(not os.environ.get("ZP_SLOW_TESTS"), reason="extended sharding modes: set ZP_SLOW_TESTS=1")
+
+
+@pytest.mark.parametrize("world,n_lookup,env", [
+    (2, 0, None), (2, 0, BUCKETS), (4, 12, BUCKETS),
+    # one coset per rank: compact per-rank copies of the key streams, dealt wire iNTTs
+    (8, 12, dict(BUCKETS, ZP_DEAL_MIN_LOG="0")),
+    pytest.param(4, 12, None, marks=_slow),
+    pytest.param(2, 0, dict(BUCKETS, ZP_SHARD_BUCKETS="0", ZP_TEST_ALLGATHER="0"), marks=_slow),
+    pytest.param(8, 0, dict(ZP_DEAL_MIN_LOG="0", ZP_COSET_COPIES="0", ZP_TEST_ALLGATHER="0"), marks=_slow)])
 def test_sharded_msm_two_ranks(pkg, oracle, tmp_path, world, n_lookup, env):
     import oracle_lib
     emu_path = pkg._build.build_emu()

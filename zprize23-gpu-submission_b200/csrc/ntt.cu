@@ -241,7 +241,8 @@ ZP_D void dif_stage_regs(fr_t x[8], int s, int sh, const NttPassParams& p) {
         if (!(e & HALF)) bfly(x[e], x[e + HALF], (((uint32_t)e & (HALF - 1)) << s) << sh, p);
 }
 
-__global__ void __launch_bounds__(128) ntt_pass8_kernel(const fr_t* __restrict__ in, fr_t* __restrict__ out, NttPassParams p) {
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) ntt_pass8_kernel(const fr_t* __restrict__ in, fr_t* __restrict__ out, NttPassParams p) {
     ZP_DYN_SMEM(uint4, sm);
     const int R = 1 << p.lr, C = 1 << p.lc, RC = R * C;  // RC == 1024
     const int RCp = (R + (R >> 3)) * C;                   // padded element count
@@ -479,18 +480,23 @@ void ntt_run(const NttTables& T, NttScratch& S, NttKind kind, int logn, const fr
             attr_set = true;
         }
 #endif
-        static const bool use_reg = !(getenv("ZP_NTT_REG") && getenv("ZP_NTT_REG")[0] == '0');
+        // ZP_NTT_REG = 4 | 5 | 6: the register-resident radix-8 kernel at that many resident CTAs per SM (128 / 102 / 85
+        // registers).  Measured SLOWER than the shared-memory radix-2 kernel at every setting (profiles/r02k_ntt_sweep.log),
+        // so it is off by default; kept for the record, parity-tested under ZP_NTT_REG=4.
+        const char* reg_env = getenv("ZP_NTT_REG");  // read per call: the tests switch it on for single transforms
+        const int use_reg = reg_env ? atoi(reg_env) : 0;
         if (use_reg && pp.lr >= 6 && RC == 1024 && threads == 128) {
-#ifndef ZP_EMU
-            static bool attr8_set = false;
-            if (!attr8_set) {
-                ZP_CUDA(cudaFuncSetAttribute(ntt_pass8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-                ZP_CUDA(cudaFuncSetAttribute(ntt_pass8_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-                attr8_set = true;
-            }
-#endif
             const size_t smem8 = (size_t)((1 << pp.lr) + (1 << (pp.lr - 3))) * (1 << pp.lc) * 32;
-            ZP_LAUNCH(ntt_pass8_kernel, dim3(grid), dim3(128), smem8, st, src, dst, pp);
+            auto launch8 = [&](auto kern) {
+#ifndef ZP_EMU
+                ZP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+                ZP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+#endif
+                ZP_LAUNCH(kern, dim3(grid), dim3(128), smem8, st, src, dst, pp);
+            };
+            if (use_reg == 6) launch8(ntt_pass8_kernel<6>);
+            else if (use_reg == 5) launch8(ntt_pass8_kernel<5>);
+            else launch8(ntt_pass8_kernel<4>);
         } else {
             ZP_LAUNCH(ntt_pass_kernel, dim3(grid), dim3(threads), smem, st, src, dst, pp);
         }

@@ -6,6 +6,7 @@
 #include "prover.cuh"
 #include "gates.cuh"
 #include <algorithm>
+#include <thread>
 
 namespace zp {
 
@@ -98,7 +99,41 @@ Prover::Prover(int logn_) : logn(logn_), n((size_t)1 << logn_), n8((size_t)8 << 
     ZP_CUDA(cudaStreamSynchronize(st));
 }
 Prover::~Prover() {
+    for (int b = 0; b < 2; b++) {
+        if (pin_buf[b]) cudaFreeHost(pin_buf[b]);
+        if (pin_ev[b]) cudaEventDestroy(pin_ev[b]);
+    }
     if (st && own_stream) cudaStreamDestroy(st);
+}
+
+static const size_t PIN_CHUNK = (size_t)64 << 20;
+void Prover::staged_h2d(void* dst_dev, const void* src_host, size_t bytes) {
+    if (bytes < ((size_t)8 << 20)) {
+        ZP_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, st));
+        return;
+    }
+    for (int b = 0; b < 2; b++)
+        if (!pin_buf[b]) {
+            ZP_CUDA(cudaMallocHost(&pin_buf[b], PIN_CHUNK));
+            ZP_CUDA(cudaEventCreate(&pin_ev[b]));
+            ZP_CUDA(cudaEventRecord(pin_ev[b], st));
+        }
+    const unsigned nthreads = std::min(4u, std::max(1u, std::thread::hardware_concurrency()));
+    int b = 0;
+    for (size_t off = 0; off < bytes; off += PIN_CHUNK, b ^= 1) {
+        const size_t len = std::min(PIN_CHUNK, bytes - off);
+        ZP_CUDA(cudaEventSynchronize(pin_ev[b]));  // the DMA that last read this staging buffer has finished
+        const char* src = (const char*)src_host + off;
+        char* dst = (char*)pin_buf[b];
+        std::vector<std::thread> pool;
+        const size_t part = (len + nthreads - 1) / nthreads;
+        for (unsigned t = 1; t < nthreads; t++)
+            if (t * part < len) pool.emplace_back([=] { memcpy(dst + t * part, src + t * part, std::min(part, len - t * part)); });
+        memcpy(dst, src, std::min(part, len));
+        for (auto& th : pool) th.join();
+        ZP_CUDA(cudaMemcpyAsync((char*)dst_dev + off, pin_buf[b], len, cudaMemcpyHostToDevice, st));
+        ZP_CUDA(cudaEventRecord(pin_ev[b], st));
+    }
 }
 void Prover::set_stream(cudaStream_t s) {
     ZP_CUDA(cudaStreamSynchronize(st));
@@ -139,7 +174,7 @@ void Prover::load_srs(const uint64_t* pts, size_t npts) {
     tab_n = 0;
     if (npts < n) throw std::runtime_error("zp_prover_load_srs: fewer than N points");
     srs.alloc(n);  // only the first N powers are ever used (load.cu:348-351)
-    ZP_CUDA(cudaMemcpyAsync(srs.p, pts, n * sizeof(affine_t), cudaMemcpyHostToDevice, st));
+    staged_h2d(srs.p, pts, n * sizeof(affine_t));
     ZP_CUDA(cudaStreamSynchronize(st));
 }
 
@@ -232,7 +267,7 @@ void Prover::load_pk(const ProverKeyC& pk, const uint64_t* coeff_len) {
     DevBuf<fr_t> stage(n8);
     for (int i = 0; i < PK_COUNT; i++) {
         // evaluations (8N): upload, drop if identically zero
-        ZP_CUDA(cudaMemcpyAsync(stage.p, pk_eval_ptr(pk, i), n8 * sizeof(fr_t), cudaMemcpyHostToDevice, st));
+        staged_h2d(stage.p, pk_eval_ptr(pk, i), n8 * sizeof(fr_t));
         bool ezero = all_zero(PS, stage.p, n8, st);
         if (ezero) {
             evals[i].release();
@@ -255,7 +290,7 @@ void Prover::load_pk(const ProverKeyC& pk, const uint64_t* coeff_len) {
                 ZP_CUDA(cudaStreamSynchronize(st));
             } else {
                 ZP_CUDA(cudaMemsetAsync(coeffs[i].p, 0, n * sizeof(fr_t), st));
-                if (len) ZP_CUDA(cudaMemcpyAsync(coeffs[i].p, pk_coeff_ptr(pk, i), len * sizeof(fr_t), cudaMemcpyHostToDevice, st));
+                if (len) staged_h2d(coeffs[i].p, pk_coeff_ptr(pk, i), len * sizeof(fr_t));
             }
         }
         ZP_CUDA(cudaStreamSynchronize(st));
@@ -868,7 +903,29 @@ void Prover::prove_resident(ProofC* out) {
             slots[cnt] = pl.slot;
             cnt++;
         }
-        { Scope s(timer, CAT_OTHER); evaluate_many(PS, polys, points, cnt, n, results, st); }
+        static const int deal_min_log = getenv("ZP_DEAL_MIN_LOG") ? atoi(getenv("ZP_DEAL_MIN_LOG")) : 16;
+        if (shard_world > 1 && allgather && logn >= deal_min_log) {
+            // multi-GPU: the evaluations are independent — dealt round-robin, the 32-byte results all-gathered (host callback)
+            Scope s(timer, CAT_OTHER);
+            const int per = (cnt + shard_world - 1) / shard_world;
+            const fr_t* my_polys[32];
+            fr_t my_points[32], my_results[32];
+            int mine = 0;
+            for (int i = shard_rank; i < cnt; i += shard_world) {
+                my_polys[mine] = polys[i];
+                my_points[mine] = points[i];
+                mine++;
+            }
+            if (mine) evaluate_many(PS, my_polys, my_points, mine, n, my_results, st);
+            std::vector<fr_t> send(per), recv((size_t)per * shard_world);
+            for (int k = 0; k < per; k++) send[k] = k < mine ? my_results[k] : fr_t::zero();
+            if (allgather(allgather_user, send.data(), recv.data(), sizeof(fr_t) * per) != 0)
+                throw std::runtime_error("all-gather of the evaluations failed");
+            for (int i = 0; i < cnt; i++) results[i] = recv[(size_t)(i % shard_world) * per + i / shard_world];
+        } else {
+            Scope s(timer, CAT_OTHER);
+            evaluate_many(PS, polys, points, cnt, n, results, st);
+        }
         for (int i = 0; i < cnt; i++) ev[slots[i]] = H(results[i]);
     }
     Fr vanishing = z_ch.pow_u64(n) - Fr::one();
@@ -967,14 +1024,24 @@ void Prover::prove_resident(ProofC* out) {
           lincomb(comb.p, lp.data(), ls.data(), (int)lp.size(), n, st);
           divide_by_linear(PS, comb.p, n, D(point), wit_out, st); }
     };
+    // multi-GPU with a device broadcast: the two witness polynomials are built by ranks 0 and 1 and broadcast
+    static const int open_deal_min_log = getenv("ZP_DEAL_MIN_LOG") ? atoi(getenv("ZP_DEAL_MIN_LOG")) : 16;
+    const bool deal_open = shard_world > 1 && dev_bcast != nullptr && logn >= open_deal_min_log;
     Fr aw = tr.challenge_scalar("aggregate_witness");
-    open({lin.p, coeffs[PK_SIGL].p, coeffs[PK_SIGR].p, coeffs[PK_SIGO].p, lookup_on ? f_poly.p : nullptr,
-          lookup_on ? h2_poly.p : nullptr, lookup_on ? table_poly.p : nullptr, w_poly[0].p, w_poly[1].p, w_poly[2].p, w_poly[3].p},
-         z_ch, aw, wit.p);
+    if (!deal_open || shard_rank == 0)
+        open({lin.p, coeffs[PK_SIGL].p, coeffs[PK_SIGR].p, coeffs[PK_SIGO].p, lookup_on ? f_poly.p : nullptr,
+              lookup_on ? h2_poly.p : nullptr, lookup_on ? table_poly.p : nullptr, w_poly[0].p, w_poly[1].p, w_poly[2].p, w_poly[3].p},
+             z_ch, aw, wit.p);
     Fr saw = tr.challenge_scalar("aggregate_witness");
-    open({z_poly.p, w_poly[0].p, w_poly[1].p, w_poly[3].p, lookup_on ? h1_poly.p : nullptr, z2_poly.p,
-          lookup_on ? table_poly.p : nullptr},
-         zs, saw, wit2.p);
+    if (!deal_open || shard_rank == 1)
+        open({z_poly.p, w_poly[0].p, w_poly[1].p, w_poly[3].p, lookup_on ? h1_poly.p : nullptr, z2_poly.p,
+              lookup_on ? table_poly.p : nullptr},
+             zs, saw, wit2.p);
+    if (deal_open) {
+        Scope s(timer, CAT_OTHER);
+        if (dev_bcast(dev_bcast_user, wit.p, n * sizeof(fr_t), 0) != 0 || dev_bcast(dev_bcast_user, wit2.p, n * sizeof(fr_t), 1) != 0)
+            throw std::runtime_error("device broadcast of an opening witness polynomial failed");
+    }
     {
         const fr_t* op[2] = {wit.p, wit2.p};
         CommitmentC* oc[2] = {&out->aw_opening, &out->saw_opening};

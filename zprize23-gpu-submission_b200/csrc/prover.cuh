@@ -94,6 +94,12 @@ struct Prover {
     bool coset_copies = true;  // ZP_COSET_COPIES=0: read the natural-order streams at stride 8 instead
     void ensure_coset_copies();
 
+    // host (pageable) -> device copies of the big key arrays go through two pinned staging buffers: a few host threads fill
+    // one while the DMA engine drains the other (a plain cudaMemcpy from pageable memory stages single-threaded)
+    void* pin_buf[2] = {nullptr, nullptr};
+    cudaEvent_t pin_ev[2] = {nullptr, nullptr};
+    void staged_h2d(void* dst_dev, const void* src_host, size_t bytes);
+
     explicit Prover(int logn_);
     ~Prover();
     void set_stream(cudaStream_t s);
