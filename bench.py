@@ -80,10 +80,11 @@ def workload_config(height, cs_n, log_n, world):
     """The `config` object of the JSON line — built by ONE function so that both arms print the same workload."""
     return {"workload": "Poseidon Merkle tree HEIGHT=%d PLONK gen_proof (cs.n=%d, domain 2^%d, zero lookup table), "
                         "witness seed 42, SRS tau seed 7" % (height, cs_n, log_n),
-            "parallelism": "1 proof over %d GPU(s): MSMs sharded by point range (192-byte partial sums all-gathered per "
-                           "commitment batch); quotient round sharded by the 8 cosets of the extended domain (size-N coset "
-                           "NTTs + fused quotient pass + coset iNTT per rank, per-coset coefficients broadcast over NCCL, "
-                           "size-8 DFT across cosets)" % world,
+            "parallelism": "1 proof over %d GPU(s): every commitment's MSM split by bucket share (cyclic over the 2^19 buckets of the "
+                           "precomputed-table Pippenger; 2 x 192-byte partial sums per member all-gathered); quotient round split "
+                           "by the 8 cosets of the extended domain (size-N coset NTTs + fused quotient pass + coset iNTT per rank, "
+                           "per-coset coefficients all-gathered over NCCL, size-8 DFT across cosets); wire iNTTs, evaluations "
+                           "and opening polynomials dealt across ranks" % world,
             "l2": "inputs larger than L2 (each polynomial 128 MiB, extended arrays 1 GiB)",
             "resident": "prover key, SRS, twiddles (and the witness for `value`) in HBM before the timed region"}
 
@@ -429,18 +430,22 @@ def main():
     # recovering 1/(x2-x1) from the shared inversion inside a 16-slot leaf group = 4.875 * 588 multiply-adds.
     DOWN0_MADS_PER_ADD = (3.0 + 15.0 / 8.0) * 588.0
     down_ach = down_pairs * DOWN0_MADS_PER_ADD / (down_ms * 1e-3) / 1e12 if down_ms > 0 else None
+    # DRAM traffic of the same kernel: dram__bytes_read.sum + dram__bytes_write.sum PER LAUNCH averaged over all its launches
+    # in one proof (one `ncu --set full` capture, profiles/r02_ncu_traffic.json) — the same scope as avg_launch_ms
     traffic = None
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")))
         if world == 1 and args.height == 15:
-            traffic = tj["ba_down0_kernel"]["traffic_bytes_per_launch"]  # bytes per launch, one ncu --set full capture
+            traffic = tj["ba_down0_kernel"]["traffic_bytes_per_launch_avg"]
     except Exception:  # noqa: BLE001
         pass
     roofline = {"bound": "int32-mad", "kernel": "ba_down0_kernel",
                 "achieved": down_ach, "peak": int_peak, "unit": "Tmad/s",
                 "frac": (down_ach / int_peak) if down_ach and int_peak else None,
                 "traffic": traffic,
-                "traffic_unit": "bytes (dram read + write, ncu --set full) of the largest launch: round 1 of the 4-member wire batch",
+                "traffic_unit": "bytes per launch (dram read + write, ncu --set full), averaged over the kernel's launches of one proof; "
+                                "algorithmic bytes per launch = pairs x (2 x 96 B points in + 96 B sum out + 48 B prefix + 4 B slot) / launches",
+                "algorithmic_bytes_per_launch": (down_pairs * (2 * 96 + 96 + 48 + 4) / max(down_launch, 1)) if down_launch else None,
                 "peak_source": "in-run dependent-free mad.lo.u32 microbenchmark (SURVEY 8d)",
                 "algorithmic_ops": "4.875 * 588 multiply-adds per affine bucket addition x additions counted on the device",
                 "launches": down_launch, "avg_launch_ms": down_ms / max(down_launch, 1),

@@ -28,7 +28,7 @@ def _free_port():
 @pytest.mark.parametrize("world,height,lookups,kind", [(2, 9, 0, 0), (2, 5, 16, 0), (4, 0, 12, 1), (8, 7, 0, 0)])
 def test_sharded_proof_on_devices_equals_oracle(gpu_lib, oracle, tmp_path, world, height, lookups, kind):
     out = str(tmp_path / "proof.npy")
-    env = dict(os.environ, ZP_DEAL_MIN_LOG="0")
+    env = dict(os.environ, ZP_DEAL_MIN_LOG="0", ZP_SHARD_BUCKETS_MIN_LOG="0")  # bucket shares / dealing also at these small sizes
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
            "--master-port", str(_free_port()), os.path.join(ROOT, "tools", "run_sharded_proof.py"), "--height", str(height),
            "--lookups", str(lookups), "--kind", str(kind), "--out", out]

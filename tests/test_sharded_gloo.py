@@ -77,7 +77,7 @@ import pytest  # noqa: E402
 
 # second and third case: the precomputed-table route, where the ranks split the BUCKET range of the MSM (every rank walks
 # all points) — with batch-affine rounds forced on at this small size, and once in the old point-range mode
-BUCKETS = {"ZP_MSM_PRECOMP_MIN_LOG": "8", "ZP_MSM_BA_MIN_LOG": "8", "ZP_MSM_BA_ROUNDS": "2"}
+BUCKETS = {"ZP_MSM_PRECOMP_MIN_LOG": "8", "ZP_MSM_BA_MIN_LOG": "8", "ZP_MSM_BA_ROUNDS": "2", "ZP_SHARD_BUCKETS_MIN_LOG": "0"}
 
 
 # the last three repeat a covered mechanism in another mode (point-range MSM shards, no compact coset copies, broadcast

@@ -1,5 +1,5 @@
 """BASELINE config 3: G1 MSM sweep 2^16 .. 2^24 on 1 / 2 / 4 / 8 B200 (one process per GPU, torchrun):
-  torchrun --nproc-per-node G tools/bench_msm_sharded.py --logs 16,18,20,22,24 [--batch 4]
+  torchrun --nproc-per-node G tools/bench_msm_sharded.py --sizes 16,18,20,22,24 [--batch 4]
 Every rank holds the SRS and the scalars; the MSM is split by bucket share (precomputed window tables, n >= 2^16) and the
 192-byte partial sums are all-gathered and folded.  Time = CUDA events on every rank, MAX over ranks; the result is
 checked against the known-trapdoor identity  MSM(s) = [sum_i s_i tau^i] G  on rank 0."""
@@ -21,7 +21,7 @@ import oracle_lib  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--logs", default="16,18,20,22")
+    ap.add_argument("--sizes", default="16,18,20,22")
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--batch", type=int, default=1)
     args = ap.parse_args()
@@ -35,7 +35,7 @@ def main():
     lib = pkg.load_library()
     orc = oracle_lib.load()
     tau = orc.random_fr(7, 1)[0]
-    for lg in [int(x) for x in args.logs.split(",")]:
+    for lg in [int(x) for x in args.sizes.split(",")]:
         n = 1 << lg
         x = orc.random_fr(2, n)
         ctx = pkg.ProverContext(max(lg, 6), lib)

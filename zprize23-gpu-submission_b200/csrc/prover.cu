@@ -394,7 +394,13 @@ host::G1 Prover::msm_over_srs(const fr_t* scalars_dev, size_t lo, size_t hi, siz
 // true when a sharded commitment of ncoef coefficients splits the BUCKETS of the precomputed-table MSM across the ranks
 // (every rank walks all points; see msm.cu) instead of the point range
 bool Prover::shard_by_buckets(size_t ncoef) const {
-    if (shard_world <= 1 || (shard_world & (shard_world - 1)) || !shard_buckets || !use_precomp || ncoef < precomp_min) return false;
+    // below 2^21 coefficients a rank's bucket share is too small for the batch-affine rounds and point ranges win
+    // (profiles/r02r_msm_sharded_sweep.jsonl: 2^20 on 8 GPUs 6.6 ms by buckets, 2.3 ms by points; 2^22: 5.3 vs 5.1 single,
+    // but 43 vs 49 ms per proof with its 4- and 6-member batches)
+    static const int min_log = getenv("ZP_SHARD_BUCKETS_MIN_LOG") ? atoi(getenv("ZP_SHARD_BUCKETS_MIN_LOG")) : 21;
+    if (shard_world <= 1 || (shard_world & (shard_world - 1)) || !shard_buckets || !use_precomp || ncoef < precomp_min ||
+        ncoef < ((size_t)1 << min_log))
+        return false;
     MsmConfig c = msm_config_precomp(srs.n, srs.n);
     return c.nbuckets / shard_world >= 256;
 }
