@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(MsmBatch batch, size_t 
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const fr_t* __restrict__ scalars = batch.s[blockIdx.y];
-    digits += (size_t)blockIdx.y * nwin * n;
+    if (digits) digits += (size_t)blockIdx.y * nwin * n;  // null: histogram only, the scatter recomputes the digits
     hist += (size_t)blockIdx.y * (one_set ? 1 : nwin) * nbuckets;
     fr_t s = load_fr(&scalars[i]).from_mont();
     uint32_t carry = 0;
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(MsmBatch batch, size_t 
             const uint32_t g = d - 1;
             d = (g & ((1u << bucket_lg) - 1)) == bucket_rank ? (g >> bucket_lg) + 1 : 0;
         }
-        digits[(size_t)w * n + i] = d | (neg << 31);
+        if (digits) digits[(size_t)w * n + i] = d | (neg << 31);
         if (d) atomicAdd(&hist[(one_set ? 0 : (size_t)w * nbuckets) + d - 1], 1u);
     }
 }
@@ -232,6 +232,47 @@ __global__ void __launch_bounds__(256) msm_scatter_kernel(const uint32_t* __rest
     uint32_t pos = atomicAdd(&cursor[set * nbuckets + d - 1], 1u);
     // with a precomputed table the entry addresses row w of the table: 2^(c w) * P_i
     sorted[pos] = (uint32_t)(tab_stride ? (size_t)w * tab_stride + i : i) | (dg & 0x80000000u);
+}
+
+// Scatter that recomputes the signed digits from the scalars instead of reading the [nwin][n] digit array (which is then
+// never written): 32 B read per scalar instead of 4 B written + 4 B read per (scalar, window) — with bucket shares 7/8 of
+// those digits are dropped anyway.  One thread per scalar, the same recoding as msm_digits_kernel.
+__global__ void __launch_bounds__(256) msm_scatter_fused_kernel(MsmBatch batch, size_t n, int c, int nwin, int nbuckets, int bucket_lg,
+                                                                uint32_t bucket_rank, size_t tab_stride,
+                                                                uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int b = blockIdx.y;
+    fr_t s = load_fr(&batch.s[b][i]).from_mont();
+    uint32_t carry = 0;
+    const uint32_t mask = (1u << c) - 1, half = 1u << (c - 1);
+    for (int w = 0; w < nwin; w++) {
+        int bit = w * c;
+        int li = bit >> 5, off = bit & 31;
+        uint32_t raw = 0;
+        if (li < 8) {
+            raw = s.l[li] >> off;
+            if (off + c > 32 && li + 1 < 8) raw |= s.l[li + 1] << (32 - off);
+            raw &= mask;
+        }
+        uint32_t d = raw + carry;
+        uint32_t neg = 0;
+        if (d > half) {
+            d = (1u << c) - d;
+            neg = 1;
+            carry = 1;
+        } else {
+            carry = 0;
+        }
+        if (d && bucket_lg) {
+            const uint32_t g = d - 1;
+            d = (g & ((1u << bucket_lg) - 1)) == bucket_rank ? (g >> bucket_lg) + 1 : 0;
+        }
+        if (!d) continue;
+        const size_t set = tab_stride ? (size_t)b : (size_t)b * nwin + w;
+        uint32_t pos = atomicAdd(&cursor[set * nbuckets + d - 1], 1u);
+        sorted[pos] = (uint32_t)(tab_stride ? (size_t)w * tab_stride + i : i) | (neg << 31);
+    }
 }
 
 // point number idx of an array whose elements are `stride` bytes apart (96: affine_t, 128: affine_pad_t)
@@ -516,14 +557,22 @@ static void msm_launch_impl(MsmWorkspace& ws, const MsmConfig& cfg, const affine
     ws.last_n = n;
     ZP_CUDA(cudaMemsetAsync(ws.cursor.p, 0, wb * sizeof(uint32_t), st));
     mark(0);
+    // no digit array, the scatter recomputes the digits (msm_scatter_fused_kernel): a win only with bucket shares, where most
+    // digits are dropped — one rank's share of 8 at 2^22 x 4: digits + scatter 1.55 -> 1.18 ms; whole MSM: 4.25 -> 4.66 ms
+    // (profiles/r02s_msm_fused_scatter.log).  ZP_MSM_FUSED_SCATTER=0|1 overrides.
+    static const int fused_env = getenv("ZP_MSM_FUSED_SCATTER") ? atoi(getenv("ZP_MSM_FUSED_SCATTER")) : -1;
+    const bool fused_scatter = fused_env >= 0 ? fused_env != 0 : cfg.bucket_lg > 0;
     if (n) {
         ZP_LAUNCH(msm_digits_kernel, dim3((unsigned)((n + 255) / 256), nbatch), dim3(256), 0, st, batch, n, cfg.c, cfg.nwin,
-                  cfg.nbuckets, cfg.bucket_lg, cfg.bucket_rank, cfg.tab_stride ? 1 : 0, ws.digits.p, ws.cursor.p);
+                  cfg.nbuckets, cfg.bucket_lg, cfg.bucket_rank, cfg.tab_stride ? 1 : 0, fused_scatter ? nullptr : ws.digits.p, ws.cursor.p);
     }
     mark(1);
     msm_scan(ws.cursor.p, ws.start.p, wb, ws.tile_sum.p, st);
     mark(2);
-    if (n) {
+    if (n && fused_scatter) {
+        ZP_LAUNCH(msm_scatter_fused_kernel, dim3((unsigned)((n + 255) / 256), nbatch), dim3(256), 0, st, batch, n, cfg.c, cfg.nwin,
+                  cfg.nbuckets, cfg.bucket_lg, cfg.bucket_rank, cfg.tab_stride, ws.cursor.p, ws.sorted.p);
+    } else if (n) {
         ZP_LAUNCH(msm_scatter_kernel, dim3((unsigned)((n + 255) / 256), cfg.nwin * nbatch), dim3(256), 0, st, ws.digits.p, n, cfg.nwin,
                   cfg.nbuckets, cfg.tab_stride, ws.cursor.p, ws.sorted.p);
     }
