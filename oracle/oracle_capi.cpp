@@ -370,11 +370,12 @@ int zpo_combine_split(size_t n, const uint64_t* t, const uint64_t* f, uint64_t* 
 
 // ---- circuit / prover / verifier context --------------------------------------------------------
 // with_pk: 0 = circuit + selector evaluations only (pk built elsewhere), 1 = full CPU preprocessing
-// kind: 0 Poseidon-Merkle tree of `height`; 1..3 the gadget circuits of build_custom_circuit (height ignored)
+// kind: 0 Poseidon-Merkle tree of `height`; 1..3 the gadget circuits of build_custom_circuit (kind 1: `height` = number of
+// repetitions of the gadget block, 0 or 1 = once)
 void* zpo_ctx_new_kind(int kind, int height, uint64_t witness_seed, uint64_t tau_seed, int n_lookup, int with_pk, int with_srs) {
     ensure_init();
     OracleCtx* c = new OracleCtx();
-    c->cs = kind == 0 ? build_merkle_circuit(height, witness_seed, n_lookup) : build_custom_circuit(kind, witness_seed, n_lookup);
+    c->cs = kind == 0 ? build_merkle_circuit(height, witness_seed, n_lookup) : build_custom_circuit(kind, witness_seed, n_lookup, height);
     size_t bound = std::max(c->cs.n(), c->cs.table.size());
     int logn = log2_ceil(bound);
     size_t N = (size_t)1 << logn;

@@ -462,7 +462,9 @@ static inline Composer build_merkle_circuit(int height, uint64_t witness_seed, i
 //     gadget tests (range.rs:213-250, logic.rs:353-400, ecc/scalar_mul/fixed_base.rs:176-215)
 //   2 no constant selector anywhere (q_c == 0): prelude + multiplications + equality + public input
 //   3 no arithmetic selector anywhere (q_arith == 0): blinding rows + range gadget cells only, no public input
-static inline Composer build_custom_circuit(int kind, uint64_t witness_seed, int n_lookup = 0) {
+// reps > 1 (kind 1 only) repeats the gadget block that many times with fresh random operands, to reach domain sizes where
+// the prover takes its production routes (precomputed-table MSM, batch-affine rounds, 3-pass NTTs)
+static inline Composer build_custom_circuit(int kind, uint64_t witness_seed, int n_lookup = 0, int reps = 1) {
     ensure_init();
     Composer cs;
     SplitMix64 rng(witness_seed);
@@ -506,8 +508,10 @@ static inline Composer build_custom_circuit(int kind, uint64_t witness_seed, int
         return cs;
     }
     // ---- kind 1
+    uint32_t digest = 0;
+    for (int rep = 0; rep < (reps < 1 ? 1 : reps); rep++) {
     // range gadget: 34 bits (padding case) and 32 bits (genesis-quad case)
-    cs.range_gate(cs.add_input(Fr::from_u64(((uint64_t)1 << 34) - 1)), 34);
+    cs.range_gate(cs.add_input(Fr::from_u64(rep ? (rng.next() & ((((uint64_t)1) << 34) - 1)) : ((uint64_t)1 << 34) - 1)), 34);
     cs.range_gate(cs.add_input(Fr::from_u64(rng.next() & 0xffffffffULL)), 32);
     // logic gadget
     uint32_t xr = cs.logic_gate(cs.add_input(Fr::from_u64(500)), cs.add_input(Fr::from_u64(357)), 10, true);
@@ -522,6 +526,10 @@ static inline Composer build_custom_circuit(int kind, uint64_t witness_seed, int
                                    0, 59, 52, 1, 1, 59, 103, 6, 169, 175, 51, 101, 234, 180, 125, 4};
     uint64_t sc[4];
     memcpy(sc, SC, 32);
+    if (rep) {
+        sc[0] ^= rng.next();
+        sc[1] ^= rng.next();
+    }
     uint32_t p1[2], p2[2], p3[2];
     fixed_base_scalar_mul(cs, cs.add_input(Fr::from_canonical(sc)), te_generator(), p1);
     uint64_t s2[4] = {rng.next(), rng.next(), rng.next(), rng.next() >> 6};
@@ -540,8 +548,9 @@ static inline Composer build_custom_circuit(int kind, uint64_t witness_seed, int
     // one Poseidon-shaped hash
     HashParams hp(0x504f534549444f4eULL);
     Fr l = rng.next_fr(), r = rng.next_fr();
-    uint32_t digest = cs.add_input(hash_native(hp, l, r));
+    digest = cs.add_input(hash_native(hp, l, r));
     hash_gadget(cs, hp, cs.add_input(l), cs.add_input(r), digest);
+    }  // reps
     if (n_lookup > 0) {
         for (uint64_t a = 0; a < 4; a++)
             for (uint64_t b = 0; b < 4; b++)

@@ -16,9 +16,12 @@
 //   KZG commit / open (SonicKZG10, no hiding)  PNP twin lib/PLONK/src/KZG/kzg10.cu:31-146
 // Parity: the Rust crate cannot be built here (no cargo; arkworks/merlin not vendored), so this
 // restatement is pinned by (1) the reference's own constants, (2) blst + the reference's strobe.cpp
-// compiled into oracle/_ref, (3) Merlin's published known-answer vector, (4) the verifier restatement
-// (zp_verifier.hpp) accepting its proofs.  No reference fixture holds proof bytes, so
-// whole-proof parity against the Rust prover itself remains "unpinned".
+// compiled into oracle/_ref, (3) Merlin's published known-answer vector, (4) the reference's own
+// unit-test vectors for combine_split, the sigma permutations and lc (tests/test_reference_vectors.py),
+// (5) the reference's NATIVE prover run on the GPU box at HEIGHT=4 (same ProofC bytes), (6) two
+// verifiers accepting its proofs: the trapdoor restatement (zp_verifier.hpp) and the product's pairing
+// verifier.  No reference fixture holds proof bytes, so whole-proof parity against the
+// RUST prover itself remains "unpinned".
 #pragma once
 #include "zp_circuit.hpp"
 #include "zp_transcript.hpp"

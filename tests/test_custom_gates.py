@@ -38,8 +38,8 @@ def test_jubjub_generator(oracle):
     assert oracle.lib.zpo_te_generator_on_curve() == 1
 
 
-def _product_matches_oracle(pkg, lib, oracle, kind, n_lookup, use_host_pk, shard=None):
-    oc = oracle_lib.OracleCircuit(oracle, 0, 42, 7, n_lookup, kind=kind)
+def _product_matches_oracle(pkg, lib, oracle, kind, n_lookup, use_host_pk, reps=0):
+    oc = oracle_lib.OracleCircuit(oracle, reps, 42, 7, n_lookup, kind=kind)
     ref_proof, _ = oc.prove()
     ctx = pkg.ProverContext(oc.log_n, lib)
     ctx.load_srs(oc.srs())
@@ -68,3 +68,12 @@ def test_emulated_product_gadget_circuits(pkg, emu_lib, oracle, kind, n_lookup, 
                                                        (2, 0, False), (2, 0, True), (3, 0, False), (3, 0, True)])
 def test_gpu_gadget_circuits(pkg, gpu_lib, oracle, kind, n_lookup, use_host_pk):
     _product_matches_oracle(pkg, gpu_lib, oracle, kind, n_lookup, use_host_pk)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("use_host_pk", [False, True])
+def test_gpu_gadget_circuit_through_production_routes(pkg, gpu_lib, oracle, use_host_pk):
+    """70 repetitions of the gadget block + 300 plookup rows: N = 2^16, so the quotient kernel with CUSTOM and LOOKUP on, the
+    custom linearisation terms and all ten 8N coset NTTs run together with the precomputed-table MSM, the batch-affine
+    rounds and the multi-pass NTTs.  The oracle needs ~5-10 s for this proof."""
+    _product_matches_oracle(pkg, gpu_lib, oracle, 1, 300, use_host_pk, reps=70)

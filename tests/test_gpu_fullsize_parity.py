@@ -35,3 +35,23 @@ def test_gen_proof_equals_pinned_oracle_proof(pkg, gpu_lib, oracle, height):
     proof, again = _prove(pkg, gpu_lib, oracle, height)
     assert np.array_equal(proof, again), "proof differs between two runs on the same context"
     assert np.array_equal(proof, np.load(path)), "device proof differs from the pinned oracle proof"
+
+
+def test_lookup_proof_through_production_routes(pkg, gpu_lib, oracle):
+    """HEIGHT=9 Merkle circuit + 2000 plookup rows (N = 2^16): compress / query table / combine_split / z2 and the lookup
+    terms of the quotient and linearisation at a size where the MSM and NTT take their production routes; expected bytes
+    from the oracle run here (a few seconds), plus acceptance by the product's pairing verifier."""
+    oc = oracle_lib.OracleCircuit(oracle, 9, 42, 7, 2000)
+    ref, _ = oc.prove()
+    ctx = pkg.ProverContext(oc.log_n, gpu_lib)
+    ctx.load_srs(oc.srs())
+    v, c, nv = oc.wiring()
+    ctx.preprocess_wiring(oc.selector_evals()[:15], v, c, nv, oc.tables())
+    circ = pkg.make_circuit(oc.cs_n, oc.lookup_len, oc.pi_pos, oc.q_lookup(), oc.pi_canonical(), *oc.wires())
+    proof = ctx.prove(circ).to_words()
+    assert np.array_equal(proof, ref)
+    ver = pkg.Verifier(oc.n, ctx.verifier_key(), pkg.g2_mul_generator(oc.tau(), gpu_lib), gpu_lib)
+    assert ver.verify(proof, oc.pi_pos, oracle.fr_op(5, oc.pi_canonical().reshape(1, 4))[0]) == (True, 3)
+    ver.close()
+    ctx.close()
+    oc.close()
