@@ -33,41 +33,45 @@ while IFS= read -r -d '' f; do
   o="_ref/pnp_obj/tu_$i.o"
   ( "$NVCC" -std=c++17 -O3 -arch=sm_100 -Xcompiler -fPIC -ccbin g++ -w -include cstdint -I"$REF/blst/include" -c "$f" -o "$o" ) &
   pids+=($!)
-  if [ "$(basename "$f")" = "zk_function.cu" ]; then
-    # DOCUMENTED PATCH (second library only; the first one stays unmodified): the reference's split_tx_poly
-    # (lib/PLONK/utils/zk_function.cu:38-48) copies 8 slices of n elements out of t_poly without checking t_poly's size; on
-    # sm_100 that cudaMemcpy faults above HEIGHT=4 (profiles/r02b_pnp_reference_crash_backtrace.log).  The patched copy
-    # (transient, under _ref/pnp_obj, deleted below) clamps every slice to what t_poly holds, zero-fills the rest and
-    # reports the sizes, so that the reference can be timed at HEIGHT=15 on the same B200.
+  case "$(basename "$f")" in quotient.cu|point.cu|msmcollect.cpp)
+    # DOCUMENTED PATCH (second library only; the first one stays unmodified).  The reference calls destructors explicitly on
+    # locals that are destroyed AGAIN at scope exit — `arithmetic_evals.~Arithmetic(); selector_evals.~Selectors();
+    # permutation_evals.~Permutation();` (lib/PLONK/src/plonk_core/src/proof_system/quotient.cu:277-278,323) and
+    # `midN.~SyncedMemory();` (lib/PLONK/src/point.cu:128-159,224-253).  Their members are std::shared_ptr (caffe/interface.hpp:9),
+    # so every buffer is released twice: undefined behaviour that ends, on this box, with the quotient polynomial's device
+    # buffer freed before split_tx_poly reads it (SIGSEGV above HEIGHT=4, profiles/r02b_pnp_reference_crash_backtrace.log;
+    # at HEIGHT=4 the stale 512 KiB block is still mapped).  The patched copy (transient, under _ref/pnp_obj, deleted below)
+    # drops the three struct destructor calls and turns `x.~SyncedMemory();` into the well-defined `x = SyncedMemory();`
+    # — the same early release, once.  Second fix, same library: msm_collect_cpu (lib/PLONK/utils/zkp/cpu/msmcollect.cpp:35)
+    # allocates its 144-byte Jacobian result as `SyncedMemory out(3 * fq_LIMBS, false)` = 18 BYTES of pinned host memory and
+    # writes 126 bytes past its end on every MSM (seen with tools/fake_cudart: "18-byte buffer written 126 bytes past its
+    # end", 33 times per proof); the patched copy sizes it 3 * fq_LIMBS * sizeof(uint64_t).  Nothing else changes, so the
+    # reference can be run and timed at HEIGHT=15.
     d="$(dirname "$f")"
-    python3 - "$f" _ref/pnp_obj/zk_function_patched.cu <<'PYEOF'
-import sys
+    b="$(basename "$f")"; x="${b##*.}"; b="${b%.*}"
+    python3 - "$f" "_ref/pnp_obj/${b}_patched.$x" <<'PYEOF'
+import re, sys
 src = open(sys.argv[1]).read()
-old = "caffe_gpu_memcpy(t_.size(), t_gpu + i*t_.size(), t_x_gpu);"
-new = ("{ size_t off = (size_t)i * t_.size(); size_t avail = off < t_poly.size() ? t_poly.size() - off : 0; "
-       "size_t cnt = avail < t_.size() ? avail : t_.size(); "
-       "cudaPointerAttributes pa, pb; cudaPointerGetAttributes(&pa, (char*)t_gpu + off); cudaPointerGetAttributes(&pb, t_x_gpu); "
-       "if (i == 0) fprintf(stderr, \"[ref-patch] split_tx_poly: t_poly holds %zu bytes, 8 slices need %zu\\n\", t_poly.size(), 8 * t_.size()); "
-       "fprintf(stderr, \"[ref-patch] slice %d: src %p (memory type %d) dst %p (memory type %d) bytes %zu\\n\", i, (char*)t_gpu + off, (int)pa.type, t_x_gpu, (int)pb.type, cnt); "
-       "cudaError_t e1 = cudaMemset(t_x_gpu, 0, t_.size()); "
-       "cudaError_t e2 = cnt ? cudaMemcpy(t_x_gpu, (char*)t_gpu + off, cnt, cudaMemcpyDeviceToDevice) : cudaSuccess; "
-       "if (e1 != cudaSuccess || e2 != cudaSuccess) fprintf(stderr, \"[ref-patch] memset: %s, memcpy: %s\\n\", cudaGetErrorString(e1), cudaGetErrorString(e2)); }")
-assert old in src
-open(sys.argv[2], "w").write(src.replace(old, new))
+out, n1 = re.subn(r"^\s*\w+\.~(Arithmetic|Selectors|Permutation)\(\);\s*$", "", src, flags=re.M)
+out, n2 = re.subn(r"(\w+)\.~SyncedMemory\(\);", r"\1 = SyncedMemory();", out)
+out, n3 = re.subn(r"SyncedMemory out\(3 \* fq_LIMBS, false\);", "SyncedMemory out(3 * fq_LIMBS * sizeof(uint64_t), false);", out)
+assert n1 + n2 + n3 > 0, "nothing to patch in " + sys.argv[1]
+sys.stderr.write("[build_pnp_ref] %s: %d struct destructor calls dropped, %d SyncedMemory destructor calls turned into resets, %d result buffers resized\n" % (sys.argv[1].split("/")[-1], n1, n2, n3))
+open(sys.argv[2], "w").write(out)
 PYEOF
     ( "$NVCC" -std=c++17 -O3 -arch=sm_100 -Xcompiler -fPIC -ccbin g++ -w -include cstdint -I"$REF/blst/include" -I"$d" \
-        -c _ref/pnp_obj/zk_function_patched.cu -o _ref/pnp_obj/patched_zk_function.o ) &
+        -c "_ref/pnp_obj/${b}_patched.$x" -o "_ref/pnp_obj/patched_${b}.obj" ) &
     pids+=($!)
-    echo "$o" > _ref/pnp_obj/zk_function_obj_name
-  fi
+    echo "$o" >> _ref/pnp_obj/patched_originals
+    ;;
+  esac
   if (( ${#pids[@]} >= ${ZP_JOBS:-8} )); then wait "${pids[0]}"; pids=("${pids[@]:1}"); fi
 done < <(find "$REF/PLONK" "$REF/caffe" "$REF/hello.cu" \( -name '*.cu' -o -name '*.cpp' \) -print0)
 wait || true
-ORIG_ZK="$(cat _ref/pnp_obj/zk_function_obj_name)"
-mv _ref/pnp_obj/patched_zk_function.o _ref/pnp_obj/patched_zk_function.obj
 "$NVCC" -shared -arch=sm_100 -o "$OUT" _ref/pnp_obj/*.o -lcudart -lpthread
-mv "$ORIG_ZK" "$ORIG_ZK.orig"
-mv _ref/pnp_obj/patched_zk_function.obj _ref/pnp_obj/patched_zk_function.o
+# second library: the same objects with the patched translation units in place of their originals
+while IFS= read -r orig; do mv "$orig" "$orig.orig"; done < _ref/pnp_obj/patched_originals
+for p in _ref/pnp_obj/patched_*.obj; do mv "$p" "${p%.obj}.o"; done
 "$NVCC" -shared -arch=sm_100 -o "$PATCHED" _ref/pnp_obj/*.o -lcudart -lpthread
 rm -rf _ref/pnp_obj
 echo "built $OUT"

@@ -641,7 +641,7 @@ static void msm_launch_impl(MsmWorkspace& ws, const MsmConfig& cfg, const affine
                 ZP_LAUNCH(ba_up0_kernel, dim3(nblk), dim3(BA_T), 0, st, ws.ba_src.p, rs + wb, cap, entries, pts, pstride, ws.ba_pre.p,
                           ws.ba_den.p, ws.ba_flag.p);
             }
-            fq_batch_inverse(ws.ba_den.p, m, ws.ba_den.p + m, st);
+            fq_batch_inverse(ws.ba_den.p, m, ws.ba_den.p + m, ws.ba_root.get(), st);
             if (stats) {
                 if (!ws.down_ev[2 * r]) {
                     ZP_CUDA(cudaEventCreate(&ws.down_ev[2 * r]));

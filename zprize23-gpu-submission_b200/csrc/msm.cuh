@@ -43,6 +43,21 @@ struct MsmBatch {
     const fr_t* s[MSM_MAX_BATCH];
 };
 
+// a few pinned host words owned by a workspace (root of the inversion tree: one 48-byte round trip per batch-affine round)
+struct PinnedFq {
+    fq_t* p = nullptr;
+    PinnedFq() = default;
+    PinnedFq(const PinnedFq&) = delete;
+    PinnedFq& operator=(const PinnedFq&) = delete;
+    ~PinnedFq() {
+        if (p) cudaFreeHost(p);
+    }
+    fq_t* get() {
+        if (!p) ZP_CUDA(cudaMallocHost((void**)&p, 2 * sizeof(fq_t)));
+        return p;
+    }
+};
+
 struct MsmWorkspace {
     DevBuf<uint32_t> digits;   // [nwin][n]   |d| | sign << 31
     DevBuf<uint32_t> sorted;   // [<= nwin*n] point index | sign << 31, grouped by (window, bucket)
@@ -67,6 +82,7 @@ struct MsmWorkspace {
     DevBuf<uint32_t> ba_cnt, ba_rs[2];
     DevBuf<uint32_t> ba_flag;     // [0] degenerate pair seen, [1] entries left for the accumulation
     uint32_t ba_flag_host[2] = {0, 0};
+    PinnedFq ba_root;             // [0] root product coming back, [1] its inverse going out
     bool ba_used = false;
     double acc_entries = 0;       // bucket entries the accumulate kernel of the last launch processed
     // arguments of the last launch (to redo it on the plain path if a degenerate pair was seen)

@@ -296,8 +296,10 @@ __global__ void __launch_bounds__(128) bi_down_kernel(fq_t* __restrict__ vals, s
 }
 
 // In place: d[i] <- 1 / d[i] for i < n (all d[i] != 0).  `levels` holds >= n/7 + 64 scratch elements.  One host round
-// trip inverts the single root product (the reference inverts every element separately, mont_arithmetic.cu:72-78).
-static void fq_batch_inverse(fq_t* d, size_t n, fq_t* levels, cudaStream_t st) {
+// trip inverts the single root product (the reference inverts every element separately, mont_arithmetic.cu:72-78):
+// the root comes back into pinned word [0], its inverse leaves from pinned word [1] — ONE stream synchronisation per call;
+// the next call's synchronisation orders the host's next write to [1] after this call's upload has been consumed.
+static void fq_batch_inverse(fq_t* d, size_t n, fq_t* levels, fq_t* pinned, cudaStream_t st) {
     std::vector<fq_t*> lv;
     std::vector<size_t> sz;
     lv.push_back(d);
@@ -310,12 +312,10 @@ static void fq_batch_inverse(fq_t* d, size_t n, fq_t* levels, cudaStream_t st) {
         sz.push_back(m);
         next += m;
     }
-    fq_t root;
-    ZP_CUDA(cudaMemcpyAsync(&root, lv.back(), sizeof(fq_t), cudaMemcpyDeviceToHost, st));
+    ZP_CUDA(cudaMemcpyAsync(&pinned[0], lv.back(), sizeof(fq_t), cudaMemcpyDeviceToHost, st));
     ZP_CUDA(cudaStreamSynchronize(st));
-    root = host::to_dev(host::to_host(root).inverse());
-    ZP_CUDA(cudaMemcpyAsync(lv.back(), &root, sizeof(fq_t), cudaMemcpyHostToDevice, st));
-    ZP_CUDA(cudaStreamSynchronize(st));  // `root` lives on this stack frame
+    pinned[1] = host::to_dev(host::to_host(pinned[0]).inverse());
+    ZP_CUDA(cudaMemcpyAsync(lv.back(), &pinned[1], sizeof(fq_t), cudaMemcpyHostToDevice, st));
     for (size_t l = lv.size() - 1; l-- > 0;) {
         size_t m = sz[l + 1];
         ZP_LAUNCH(bi_down_kernel, dim3((unsigned)((m + 127) / 128)), dim3(128), 0, st, lv[l], sz[l], lv[l + 1]);
