@@ -207,7 +207,8 @@ int zp_prover_set_device_broadcast(zp_prover* p, zp_dev_broadcast_fn bcast, void
 typedef int (*zp_dev_allgather_fn)(void* user, void* dev_base, size_t bytes_per_rank);
 int zp_prover_set_device_allgather(zp_prover* p, zp_dev_allgather_fn allgather, void* user);
 /* Device-milliseconds of the phases of the last proof: [0] total, [1] NTT, [2] MSM, [3] quotient,
- * [4] other (CUDA events on the prover's stream). */
+ * [4] other (CUDA events on the prover's stream); [5] (n >= 6) wall time of the coset NTTs that ran on the prover's second,
+ * low-priority stream concurrently with the commitment MSMs (single GPU; not part of [1]). */
 int zp_prover_last_timing(zp_prover* p, double* out_ms, int n);
 
 /* ---- ark-serialize 0.3 wire format of `Proof<Fr, KZG10<Bls12_381>>` (proof.rs:37-121) --------------------------

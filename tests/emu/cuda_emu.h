@@ -100,6 +100,10 @@ static inline cudaError_t cudaDeviceSynchronize() { return 0; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
 static inline cudaError_t cudaStreamCreate(cudaStream_t* s) { *s = 0; return 0; }
 static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
+enum { cudaStreamDefault = 0, cudaStreamNonBlocking = 1 };
+static inline cudaError_t cudaStreamCreateWithPriority(cudaStream_t* s, unsigned, int) { *s = 0; return 0; }
+static inline cudaError_t cudaDeviceGetStreamPriorityRange(int* least, int* greatest) { *least = 0; *greatest = -1; return 0; }
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return 0; }
 static inline cudaError_t cudaGetLastError() { return 0; }
 static inline cudaError_t cudaPeekAtLastError() { return 0; }
 static inline const char* cudaGetErrorString(cudaError_t) { return "emu"; }

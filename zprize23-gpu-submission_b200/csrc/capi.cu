@@ -188,7 +188,7 @@ int zp_prover_set_device_allgather(zp_prover* p, zp_dev_allgather_fn fn, void* u
 }
 int zp_prover_last_timing(zp_prover* p, double* out_ms, int n) {
     return guard([&] {
-        for (int i = 0; i < n && i < 5; i++) out_ms[i] = P(p)->last_ms[i];
+        for (int i = 0; i < n && i < 6; i++) out_ms[i] = P(p)->last_ms[i];
     });
 }
 

@@ -391,6 +391,9 @@ const fr_t* NttTables::pass_table(int logn, int inverse, int lr, int lk, cudaStr
         DevBuf<fr_t> b((size_t)1 << (lr + lk));
         size_t cnt = (size_t)1 << (lr + lk);
         ZP_LAUNCH(ntt_pass_table_kernel, dim3((unsigned)((cnt + 255) / 256)), dim3(256), 0, st, b.p, lr, lk, inverse, w_lo.p, w_hi.p);
+        // built once per context; transforms run on two streams (Prover::st / st2), so the table is complete before ANY
+        // stream can see its pointer
+        ZP_CUDA(cudaStreamSynchronize(st));
         it = direct.emplace(key, std::move(b)).first;
     }
     return it->second.p;
@@ -404,6 +407,7 @@ const fr_t* NttTables::coset_out_table(int logn, cudaStream_t st) const {
         DevBuf<fr_t> b(cnt);
         ZP_LAUNCH(ntt_coset_out_table_kernel, dim3((unsigned)((cnt + 255) / 256)), dim3(256), 0, st, b.p, cnt, ninv[logn], gi_lo.p,
                   gi_hi.p);
+        ZP_CUDA(cudaStreamSynchronize(st));
         it = direct.emplace(key, std::move(b)).first;
     }
     return it->second.p;

@@ -84,7 +84,21 @@ Prover::Prover(int logn_) : logn(logn_), n((size_t)1 << logn_), n8((size_t)8 << 
         fprintf(stderr, "[zprize_b200] L2 fetch granularity set to %zu\n", got);
     }
 #endif
-    ZP_CUDA(cudaStreamCreate(&st));
+    {
+        int least = 0, greatest = 0;
+        ZP_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        ZP_CUDA(cudaStreamCreateWithPriority(&st, cudaStreamDefault, greatest));
+        // ZP_NTT_OVERLAP_PRIO: measurement knob — priority of the second stream (default: the lowest)
+        const char* pr = getenv("ZP_NTT_OVERLAP_PRIO");
+        ZP_CUDA(cudaStreamCreateWithPriority(&st2, cudaStreamNonBlocking, pr ? atoi(pr) : least));
+        for (int k = 0; k < 2; k++) {
+            ZP_CUDA(cudaEventCreate(&fork_ev[k]));
+            ZP_CUDA(cudaEventCreate(&join_ev[k]));
+        }
+        for (int k = 0; k < 4; k++) ZP_CUDA(cudaEventCreate(&ov_ev[k]));
+        const char* ov = getenv("ZP_NTT_OVERLAP");
+        if (ov && ov[0] == '0') ntt_overlap = false;
+    }
     T.init(st);
     PS.init();
     if (msm_only) {
@@ -103,7 +117,29 @@ Prover::~Prover() {
         if (pin_buf[b]) cudaFreeHost(pin_buf[b]);
         if (pin_ev[b]) cudaEventDestroy(pin_ev[b]);
     }
+    if (st2) {
+        cudaStreamSynchronize(st2);
+        cudaStreamDestroy(st2);
+    }
+    for (int k = 0; k < 2; k++) {
+        if (fork_ev[k]) cudaEventDestroy(fork_ev[k]);
+        if (join_ev[k]) cudaEventDestroy(join_ev[k]);
+    }
+    for (int k = 0; k < 4; k++)
+        if (ov_ev[k]) cudaEventDestroy(ov_ev[k]);
     if (st && own_stream) cudaStreamDestroy(st);
+}
+
+// Forks `count` coset NTTs N -> 8N onto the low-priority stream: they start when everything enqueued on `st` so far (the
+// coefficients) is done, and signal join_ev[slot]; the quotient round waits for it.  ov_ev[2 slot], ov_ev[2 slot + 1]
+// bracket the work on st2 for the phase report.
+void Prover::fork_coset_ntts(int slot, const fr_t* const* in, fr_t* const* out, int count) {
+    ZP_CUDA(cudaEventRecord(fork_ev[slot], st));
+    ZP_CUDA(cudaStreamWaitEvent(st2, fork_ev[slot], 0));
+    ZP_CUDA(cudaEventRecord(ov_ev[2 * slot], st2));
+    for (int k = 0; k < count; k++) ntt_run(T, NS2, NTT_COSET_FWD, logn + 3, in[k], n, out[k], st2);
+    ZP_CUDA(cudaEventRecord(ov_ev[2 * slot + 1], st2));
+    ZP_CUDA(cudaEventRecord(join_ev[slot], st2));
 }
 
 static const size_t PIN_CHUNK = (size_t)64 << 20;
@@ -618,6 +654,8 @@ void Prover::prove_resident(ProofC* out) {
     MW.timing = collect_msm_stats;
     struct TimingOff { MsmWorkspace& w; ~TimingOff() { w.timing = false; } } timing_off{MW};
 
+    const bool overlap = ntt_overlap && shard_world == 1 && !msm_only;
+
     MerlinTranscript tr(label);
     Fr pi_val = Fr::from_canonical(wit_pi);  // CircuitC.pi is canonical (prover.rs:721-725)
     std::vector<std::pair<uint64_t, Fr>> pis;
@@ -648,6 +686,10 @@ void Prover::prove_resident(ProofC* out) {
             }
             wp[k] = w_poly[k].p;
             wc[k] = &comm[k];
+        }
+        if (overlap) {
+            fr_t* w8p[4] = {w8[0].p, w8[1].p, w8[2].p, w8[3].p};
+            fork_coset_ntts(0, wp, w8p, 4);
         }
         commit_batch(wp, 4, n, wc, x, y, inf);
         for (int k = 0; k < 4; k++) tr.append_point(wl[k], x[k], y[k], inf[k]);
@@ -708,6 +750,11 @@ void Prover::prove_resident(ProofC* out) {
           ratio_inplace(num.p, den.p, comb.p, n, st);
           exclusive_prefix_product(PS, den.p, num.p, n, st); }
         { Scope s(timer, CAT_NTT); ntt_run(T, NS, NTT_INV, logn, num.p, n, z_poly.p, st); }
+        if (overlap) {
+            const fr_t* zin[1] = {z_poly.p};
+            fr_t* zout[1] = {z8.p};
+            fork_coset_ntts(1, zin, zout, 1);
+        }
         Fq x, y; bool inf;
         commit(z_poly.p, n, &comm[4], &x, &y, &inf);
         tr.append_point("z", x, y, inf);
@@ -771,7 +818,12 @@ void Prover::prove_resident(ProofC* out) {
         }
         { Scope s(timer, CAT_NTT);
           if (!dist) {
-              for (size_t k = 0; k < jobs.size(); k++) ntt_run(T, NS, NTT_COSET_FWD, logn + 3, jobs[k].in, n, jobs[k].out, st);
+              // jobs 0..4 (wires, z) were forked onto st2 in rounds 1 and 3 when `overlap` is set: join them here
+              for (size_t k = overlap ? 5 : 0; k < jobs.size(); k++) ntt_run(T, NS, NTT_COSET_FWD, logn + 3, jobs[k].in, n, jobs[k].out, st);
+              if (overlap) {
+                  ZP_CUDA(cudaStreamWaitEvent(st, join_ev[0], 0));
+                  ZP_CUDA(cudaStreamWaitEvent(st, join_ev[1], 0));
+              }
           } else {
               if (cs_tmp.n < n) cs_tmp.alloc(n);
               if (pj8.n < n8) pj8.alloc(n8);
@@ -1058,6 +1110,14 @@ void Prover::prove_resident(ProofC* out) {
     proof_timer.end(total_id);
     proof_timer.collect(last_ms);
     last_ms[CAT_OTHER] = last_ms[CAT_TOTAL] - last_ms[CAT_NTT] - last_ms[CAT_MSM] - last_ms[CAT_QUOT];
+    last_ms[5] = 0;
+    if (overlap) {  // st has waited for both join events and collect() synchronised st: the st2 events are complete
+        for (int k = 0; k < 2; k++) {
+            float ms = 0;
+            ZP_CUDA(cudaEventElapsedTime(&ms, ov_ev[2 * k], ov_ev[2 * k + 1]));
+            last_ms[5] += ms;
+        }
+    }
 }
 
 }  // namespace zp

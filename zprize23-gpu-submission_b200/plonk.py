@@ -518,9 +518,9 @@ class ProverContext:
         self._ck(self.lib.zp_prover_set_device_allgather(self.h, self._ag, None))
 
     def last_timing(self):
-        out = (ctypes.c_double * 5)()
-        self._ck(self.lib.zp_prover_last_timing(self.h, out, 5))
-        return dict(zip(["total_ms", "ntt_ms", "msm_ms", "quotient_ms", "other_ms"], list(out)))
+        out = (ctypes.c_double * 6)()
+        self._ck(self.lib.zp_prover_last_timing(self.h, out, 6))
+        return dict(zip(["total_ms", "ntt_ms", "msm_ms", "quotient_ms", "other_ms", "ntt_overlapped_ms"], list(out)))
 
     # ---- operator entry points (function.cuh:45-113 equivalents) ----
     def ntt(self, kind, data):
