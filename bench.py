@@ -276,15 +276,7 @@ def main():
     # ---- synthetic workload: Poseidon-shaped Merkle tree circuit, seeds of SURVEY §8d
     oc = oracle_lib.OracleCircuit(orc, args.height, 42, 7, 0, with_pk=False, with_srs=False)
     ctx = pkg.ProverContext(oc.log_n, lib)
-    # The prover's stream: a HIGH-priority torch stream, made current so that the NCCL hooks and the timing events are ordered
-    # on it.  The prover's internal second stream (lowest priority: the challenge-independent coset NTTs of a single-GPU
-    # proof, forked to run concurrently with the commitment MSMs) only fills what the MSM pipeline leaves idle.
-    # Sharded runs keep torch's default stream (that path has no second stream).
-    if world == 1:
-        stream = torch.cuda.Stream(priority=-1)
-        torch.cuda.set_stream(stream)
-    else:
-        stream = torch.cuda.current_stream()
+    stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
     ctx.generate_srs(oc.tau())
     sel = oc.selector_evals()
@@ -360,7 +352,7 @@ def main():
     acc_ms = acc_mads = exec_mads = down_ms = down_pairs = 0.0
     acc_launch = acc_commits = down_launch = 0
     # ntt_ms / msm_ms / quotient_ms / other_ms partition the step on the prover's stream; ntt_overlapped_ms is the wall time of
-    # the coset NTTs that ran on its second stream concurrently with the MSM phase (not part of ntt_ms)
+    # coset NTTs on the prover's second stream (experiment ZP_NTT_OVERLAP=1, off by default: 0 here)
     phase = {"ntt_ms": 0.0, "msm_ms": 0.0, "quotient_ms": 0.0, "other_ms": 0.0, "ntt_overlapped_ms": 0.0}
     per_step_s = []
     for _ in range(args.steps):

@@ -37,6 +37,18 @@ def test_gen_proof_equals_pinned_oracle_proof(pkg, gpu_lib, oracle, height):
     assert np.array_equal(proof, np.load(path)), "device proof differs from the pinned oracle proof"
 
 
+def test_gen_proof_with_second_stream_ntts(pkg, gpu_lib, oracle, monkeypatch):
+    """ZP_NTT_OVERLAP=1 (experiment, off by default): the coset NTTs of the wires and of z(X) run on the prover's second stream
+    concurrently with the commitment MSMs and are joined by events before the quotient pass — same proof bytes."""
+    path = os.path.join(G, "proof_height12_w42_tau7.npy")
+    if not os.path.exists(path):
+        pytest.skip("fixture not generated")
+    monkeypatch.setenv("ZP_NTT_OVERLAP", "1")  # read when the context is created
+    proof, again = _prove(pkg, gpu_lib, oracle, 12)
+    assert np.array_equal(proof, again)
+    assert np.array_equal(proof, np.load(path))
+
+
 def test_lookup_proof_through_production_routes(pkg, gpu_lib, oracle):
     """HEIGHT=9 Merkle circuit + 2000 plookup rows (N = 2^16): compress / query table / combine_split / z2 and the lookup
     terms of the quotient and linearisation at a size where the MSM and NTT take their production routes; expected bytes

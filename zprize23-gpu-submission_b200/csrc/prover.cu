@@ -97,7 +97,7 @@ Prover::Prover(int logn_) : logn(logn_), n((size_t)1 << logn_), n8((size_t)8 << 
         }
         for (int k = 0; k < 4; k++) ZP_CUDA(cudaEventCreate(&ov_ev[k]));
         const char* ov = getenv("ZP_NTT_OVERLAP");
-        if (ov && ov[0] == '0') ntt_overlap = false;
+        ntt_overlap = ov && ov[0] == '1';
     }
     T.init(st);
     PS.init();

@@ -26,14 +26,16 @@ struct Prover {
     cudaStream_t st = 0;
     bool own_stream = true;
     std::string label = "Merkle tree";
-    // Second stream, lowest priority (the prover's own stream is created with the highest): the extended-domain coset NTTs of
-    // the wire polynomials and of z(X) need no challenge, so they are forked as soon as the coefficients exist and run
-    // concurrently with the commitment MSMs, whose DRAM-latency-bound gathers, inversion-tree tops, scans and host round
-    // trips leave the integer multiplier idle ~27 % of the time.  Joined by events before the quotient pass.  Single GPU only
-    // (the sharded quotient round transforms per coset).  ZP_NTT_OVERLAP=0 disables.
+    // EXPERIMENT, off by default (ZP_NTT_OVERLAP=1 enables; parity-green, measured 0.9 % SLOWER at HEIGHT=15,
+    // profiles/r02w_ntt_overlap_second_stream.log).  Second stream, lowest priority (the prover's own stream is created with
+    // the highest): the extended-domain coset NTTs of the wire polynomials and of z(X) need no challenge, so they are forked
+    // as soon as the coefficients exist, run concurrently with the commitment MSMs and are joined by events before the
+    // quotient pass.  Single GPU only (the sharded quotient round transforms per coset).  Why it does not pay: the MSM kernels
+    // fill the SMs (registers / thread slots) even while they wait on DRAM, and both workloads are bound by the same integer
+    // multiplier — the NTT CTAs only get the slots the MSM gives up, and the MSM phase grows by what the NTT phase shrinks.
     cudaStream_t st2 = 0;
     cudaEvent_t fork_ev[2] = {nullptr, nullptr}, join_ev[2] = {nullptr, nullptr}, ov_ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    bool ntt_overlap = true;
+    bool ntt_overlap = false;
     NttScratch NS2;                  // ping-pong scratch of the transforms on st2
     void fork_coset_ntts(int slot, const fr_t* const* in, fr_t* const* out, int count);
     NttTables T;
