@@ -469,35 +469,64 @@ __global__ void __launch_bounds__(128) msm_weighted_kernel(const xyzz_t* __restr
     if (threadIdx.x == 0) store_xyzz(&partial[blockIdx.x], sm[0]);
 }
 
-// one window row of the precomputed table: dst[i] = 2^c * src[i]  (c doublings in XYZZ, one inversion); c == 0 copies
-__global__ void __launch_bounds__(128) msm_table_row_kernel(affine_pad_t* __restrict__ dst, const affine_t* __restrict__ src,
-                                                            uint32_t src_stride, size_t n, int c) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    affine_t p = load_affine(point_at(src, (uint32_t)i, src_stride));
-    if (c > 0) {
-        xyzz_t a;
-        a.set_double_affine(p.x, p.y);
-        for (int k = 1; k < c; k++) a.dbl_inplace();
-        // the group has prime order, so 2^c * P is finite for finite P
-        fq_t inv = (a.ZZ * a.ZZZ).inverse();
-        fq_t zz_inv = inv * a.ZZZ, zzz_inv = inv * a.ZZ;
-        p.x = a.X * zz_inv;
-        p.y = a.Y * zzz_inv;
-    }
-    store_fq(&dst[i].x, p.x);
-    store_fq(&dst[i].y, p.y);
-}
-void msm_build_table(affine_pad_t* dst, const affine_t* src, size_t n, int c, int nwin, cudaStream_t st) {
-    ZP_LAUNCH(msm_table_row_kernel, dim3((unsigned)((n + 127) / 128)), dim3(128), 0, st, dst, src, (uint32_t)sizeof(affine_t), n, 0);
-    for (int w = 1; w < nwin; w++)
-        ZP_LAUNCH(msm_table_row_kernel, dim3((unsigned)((n + 127) / 128)), dim3(128), 0, st, dst + (size_t)w * n,
-                  reinterpret_cast<const affine_t*>(dst + (size_t)(w - 1) * n), (uint32_t)sizeof(affine_pad_t), n, c);
-}
-
 }  // namespace zp
 #include "msm_affine.cuh"
 namespace zp {
+
+// ---- precomputed window table T[w][i] = 2^(c w) * P_i, one row from the previous one.
+// Row w is c doublings of row w - 1 in XYZZ (msm_table_dbl_kernel), then back to affine with ONE shared inversion per row:
+// z_i = ZZ_i * ZZZ_i goes through the batch inversion of the batch-affine rounds (3 products per point + one host round
+// trip) instead of a 570-product Fermat inversion per point — 735 -> 170 products per table entry, the 6.5 GiB table of a
+// 2^22-point SRS builds in a quarter of the time (it is most of a context's cold first call).
+__global__ void __launch_bounds__(128) msm_table_copy_kernel(affine_pad_t* __restrict__ dst, const affine_t* __restrict__ src, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    store_fq(&dst[i].x, load_fq(&src[i].x));
+    store_fq(&dst[i].y, load_fq(&src[i].y));
+}
+__global__ void __launch_bounds__(128) msm_table_dbl_kernel(const affine_pad_t* __restrict__ prev, size_t n, int c,
+                                                            xyzz_t* __restrict__ tmp, fq_t* __restrict__ z) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const fq_t x = load_fq(&prev[i].x), y = load_fq(&prev[i].y);
+    xyzz_t a;
+    a.set_double_affine(x, y);
+    for (int k = 1; k < c; k++) a.dbl_inplace();
+    store_xyzz(&tmp[i], a);
+    // the group has prime order, so 2^c * P is finite for a finite P on the curve; anything else (a caller's (0, 0)) ends
+    // with ZZ = 0 and must not poison the shared inversion: it takes part as 1 and is written back as (0, 0)
+    fq_t zz = a.ZZ * a.ZZZ;
+    store_fq(&z[i], zz.is_zero() ? fq_t::one() : zz);
+}
+__global__ void __launch_bounds__(128) msm_table_affine_kernel(affine_pad_t* __restrict__ dst, const xyzz_t* __restrict__ tmp,
+                                                               const fq_t* __restrict__ zinv, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const xyzz_t a = load_xyzz(&tmp[i]);
+    fq_t x = fq_t::zero(), y = fq_t::zero();
+    if (!a.is_inf()) {
+        const fq_t inv = load_fq(&zinv[i]);  // 1 / (ZZ * ZZZ)
+        x = a.X * (inv * a.ZZZ);             // X / ZZ
+        y = a.Y * (inv * a.ZZ);              // Y / ZZZ
+    }
+    store_fq(&dst[i].x, x);
+    store_fq(&dst[i].y, y);
+}
+void msm_build_table(affine_pad_t* dst, const affine_t* src, size_t n, int c, int nwin, cudaStream_t st) {
+    if (!n) return;
+    const dim3 grid((unsigned)((n + 127) / 128)), block(128);
+    ZP_LAUNCH(msm_table_copy_kernel, grid, block, 0, st, dst, src, n);
+    if (nwin <= 1) return;
+    DevBuf<xyzz_t> tmp(n);
+    DevBuf<fq_t> z(n + n / (BI_CH - 1) + 64);  // the values, followed by the upper levels of the inversion tree
+    PinnedFq root;
+    for (int w = 1; w < nwin; w++) {
+        ZP_LAUNCH(msm_table_dbl_kernel, grid, block, 0, st, dst + (size_t)(w - 1) * n, n, c, tmp.p, z.p);
+        fq_batch_inverse(z.p, n, z.p + n, root.get(), st);
+        ZP_LAUNCH(msm_table_affine_kernel, grid, block, 0, st, dst + (size_t)w * n, tmp.p, z.p, n);
+    }
+    ZP_CUDA(cudaStreamSynchronize(st));  // tmp / z / root die with this frame
+}
 
 // final[set] = sum_g partial[set * groups + g]   (one CTA per bucket set)
 __global__ void __launch_bounds__(128) msm_final_kernel(const xyzz_t* __restrict__ partial, int groups, xyzz_t* __restrict__ final_out) {
