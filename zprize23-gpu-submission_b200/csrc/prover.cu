@@ -154,7 +154,9 @@ void Prover::staged_h2d(void* dst_dev, const void* src_host, size_t bytes) {
             ZP_CUDA(cudaEventCreate(&pin_ev[b]));
             ZP_CUDA(cudaEventRecord(pin_ev[b], st));
         }
-    const unsigned nthreads = std::min(4u, std::max(1u, std::thread::hardware_concurrency()));
+    // host threads that fill a staging buffer (ZP_H2D_THREADS; default 8 or what the machine has)
+    static const unsigned h2d_env = getenv("ZP_H2D_THREADS") ? (unsigned)atoi(getenv("ZP_H2D_THREADS")) : 8u;
+    const unsigned nthreads = std::max(1u, std::min(h2d_env, std::max(1u, std::thread::hardware_concurrency())));
     int b = 0;
     for (size_t off = 0; off < bytes; off += PIN_CHUNK, b ^= 1) {
         const size_t len = std::min(PIN_CHUNK, bytes - off);
