@@ -43,7 +43,8 @@ struct MsmBatch {
     const fr_t* s[MSM_MAX_BATCH];
 };
 
-// a few pinned host words owned by a workspace (root of the inversion tree: one 48-byte round trip per batch-affine round)
+// a few pinned host words owned by a workspace (top level of the inversion tree, <= 256 nodes: one round trip per
+// batch-affine round; [0, 256) coming back, [256, 512) going out)
 struct PinnedFq {
     fq_t* p = nullptr;
     PinnedFq() = default;
@@ -53,7 +54,7 @@ struct PinnedFq {
         if (p) cudaFreeHost(p);
     }
     fq_t* get() {
-        if (!p) ZP_CUDA(cudaMallocHost((void**)&p, 2 * sizeof(fq_t)));
+        if (!p) ZP_CUDA(cudaMallocHost((void**)&p, 512 * sizeof(fq_t)));
         return p;
     }
 };
@@ -82,7 +83,7 @@ struct MsmWorkspace {
     DevBuf<uint32_t> ba_cnt, ba_rs[2];
     DevBuf<uint32_t> ba_flag;     // [0] degenerate pair seen, [1] entries left for the accumulation
     uint32_t ba_flag_host[2] = {0, 0};
-    PinnedFq ba_root;             // [0] root product coming back, [1] its inverse going out
+    PinnedFq ba_root;             // top level of the inversion tree: products coming back, inverses going out
     bool ba_used = false;
     double acc_entries = 0;       // bucket entries the accumulate kernel of the last launch processed
     // arguments of the last launch (to redo it on the plain path if a degenerate pair was seen)
