@@ -1,4 +1,4 @@
-# round 2, final single-GPU state: batch-inverted MSM window table, 8 staging threads, NTT overlap off by default
+# round 2, final single-GPU state: batch-inverted MSM window table, 8 staging threads, NTT overlap off by default, top of the inversion tree on the host (second run: r2y)
 mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -q -m gpu --durations=6 > gpurun_out/r2x_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r2x_pytest_gpu.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2x_smoke.log 2>&1; tail -1 gpurun_out/r2x_smoke.log
