@@ -118,6 +118,11 @@ def test_msm_batch_affine_rounds(pkg, emu_lib, oracle, monkeypatch, rounds):
     pts2[10:40] = pts2[10]
     sc2[10:40] = sc2[10]
     assert np.array_equal(ctx.msm_points(pts2, sc2, 6), oracle.msm(pts2, sc2))
+    # skewed scalars over distinct points: 500 of 700 scalars are 3, so one bucket run has 250 pairs (written by the whole
+    # warp in ba_slots_kernel) and is still split into more than 8 work segments afterwards (msm_fold_kernel's work list)
+    sc3 = sc.copy()
+    sc3[100:600] = _fr_small(oracle, [3])[0]
+    assert np.array_equal(ctx.msm_points(pts, sc3, 6), oracle.msm(pts, sc3))
     ctx.close()
 
 

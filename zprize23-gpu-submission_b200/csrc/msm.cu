@@ -89,7 +89,8 @@ void MsmWorkspace::reserve(size_t n, const MsmConfig& cfg, int nbatch) {
         const char* bm = getenv("ZP_MSM_BA_MIN_LOG");
         if (bm) ba_min_entries = (size_t)1 << atoi(bm);
     }
-    if (!counter.p) counter.alloc(1);
+    if (!counter.p) counter.alloc(2);  // [0] segment counter of the accumulate kernel, [1] length of fold_list
+    if (fold_list.n < wb) fold_list.alloc(wb);
     size_t nsets = (size_t)nbatch * cfg.nsets;
     size_t np = nsets * msm_reduce_groups(cfg);
     if (partial.n < np) partial.alloc(np);
@@ -362,41 +363,51 @@ __global__ void __launch_bounds__(128, MINBLOCKS) msm_accumulate_kernel(const af
 }
 
 // Buckets split into a few work segments (the common case on small / sharded inputs) are folded by one THREAD each
-// (all lanes busy); long runs (skewed digit distributions) by one warp each in msm_fold_kernel.
+// (all lanes busy); long runs (skewed digit distributions) are appended to a work list and folded by one warp each in
+// msm_fold_kernel, launched with a fixed grid (one warp per BUCKET used to cost 0.7 ms per pipeline in CTAs that returned
+// at once).
 static const uint32_t FOLD_SERIAL_MAX = 8;
-__global__ void __launch_bounds__(128) msm_fold_small_kernel(xyzz_t* __restrict__ segs, const uint32_t* __restrict__ seg_start, size_t nb) {
+__global__ void __launch_bounds__(128) msm_fold_small_kernel(xyzz_t* __restrict__ segs, const uint32_t* __restrict__ seg_start, size_t nb,
+                                                             uint32_t* __restrict__ long_list, uint32_t* __restrict__ long_count) {
     size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nb) return;
     uint32_t s0 = seg_start[b], s1 = seg_start[b + 1];
-    if (s1 - s0 < 2 || s1 - s0 > FOLD_SERIAL_MAX) return;
+    if (s1 - s0 < 2) return;
+    if (s1 - s0 > FOLD_SERIAL_MAX) {
+        long_list[atomicAdd(long_count, 1u)] = (uint32_t)b;
+        return;
+    }
     xyzz_t acc = load_xyzz(&segs[s0]);
     for (uint32_t s = s0 + 1; s < s1; s++) acc.add(load_xyzz(&segs[s]));
     store_xyzz(&segs[s0], acc);
 }
 
-// Buckets that were split into several work segments are folded back by one warp each (lanes stride over
-// the segment sums, then a shared-memory tree); afterwards segs[seg_start[b]] holds the whole bucket.
-__global__ void __launch_bounds__(128) msm_fold_kernel(xyzz_t* __restrict__ segs, const uint32_t* __restrict__ seg_start, size_t nb) {
+// The listed buckets are folded back by one warp each (lanes stride over the segment sums, then a shared-memory tree);
+// afterwards segs[seg_start[b]] holds the whole bucket.
+__global__ void __launch_bounds__(128) msm_fold_kernel(xyzz_t* __restrict__ segs, const uint32_t* __restrict__ seg_start,
+                                                       const uint32_t* __restrict__ long_list, const uint32_t* __restrict__ long_count) {
     __shared__ xyzz_t sm[128];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    size_t b = (size_t)blockIdx.x * 4 + warp;
-    if (b >= nb) return;
-    uint32_t s0 = seg_start[b], s1 = seg_start[b + 1];
-    if (s1 - s0 <= FOLD_SERIAL_MAX) return;  // warp-uniform; short runs were folded by msm_fold_small_kernel
-    xyzz_t acc = xyzz_t::infinity();
-    for (uint32_t s = s0 + lane; s < s1; s += 32) acc.add(load_xyzz(&segs[s]));
+    const uint32_t count = *long_count;
     xyzz_t* w = sm + warp * 32;
-    w[lane] = acc;
-    __syncwarp();
-    for (int d = 16; d >= 1; d >>= 1) {
-        if (lane < d) {
-            xyzz_t a = w[lane];
-            a.add(w[lane + d]);
-            w[lane] = a;
+    for (uint32_t i = blockIdx.x * 4 + warp; i < count; i += gridDim.x * 4) {  // warp-uniform
+        const uint32_t b = long_list[i];
+        const uint32_t s0 = seg_start[b], s1 = seg_start[b + 1];
+        xyzz_t acc = xyzz_t::infinity();
+        for (uint32_t s = s0 + lane; s < s1; s += 32) acc.add(load_xyzz(&segs[s]));
+        w[lane] = acc;
+        __syncwarp();
+        for (int d = 16; d >= 1; d >>= 1) {
+            if (lane < d) {
+                xyzz_t a = w[lane];
+                a.add(w[lane + d]);
+                w[lane] = a;
+            }
+            __syncwarp();
         }
+        if (lane == 0) store_xyzz(&segs[s0], w[0]);
         __syncwarp();
     }
-    if (lane == 0) store_xyzz(&segs[s0], w[0]);
 }
 
 ZP_D xyzz_t load_bucket(const xyzz_t* __restrict__ segs, const uint32_t* __restrict__ seg_start, size_t b) {
@@ -647,7 +658,7 @@ static void msm_launch_impl(MsmWorkspace& ws, const MsmConfig& cfg, const affine
             size_t m = (size_t)nblk * BA_T;
             ZP_LAUNCH(ba_pair_count_kernel, dim3((unsigned)((wb + 255) / 256)), dim3(256), 0, st, run_begin, run_end, wb, ws.ba_cnt.p);
             msm_scan(ws.ba_cnt.p, rs, wb, ws.tile_sum.p, st);
-            ZP_LAUNCH(ba_slots_kernel, dim3((unsigned)((wb * 32 + 255) / 256)), dim3(256), 0, st, run_begin, run_end, rs, wb,
+            ZP_LAUNCH(ba_slots_kernel, dim3((unsigned)((wb * 8 + 255) / 256)), dim3(256), 0, st, run_begin, run_end, rs, wb,
                       ws.ba_src.p);
             static const int ba_pf = getenv("ZP_BA_PF") ? atoi(getenv("ZP_BA_PF")) : 0;
             static const int ba_ng = getenv("ZP_BA_NG") ? atoi(getenv("ZP_BA_NG")) : 1;
@@ -726,8 +737,11 @@ static void msm_launch_impl(MsmWorkspace& ws, const MsmConfig& cfg, const affine
             ZP_LAUNCH(k, dim3(grid), dim3(128), 0, st, pts, pstride, entries, ws.desc.p, ws.seg_start.p + wb, ws.counter.p, ws.segs.p);
         }
     }
-    ZP_LAUNCH(msm_fold_small_kernel, dim3((unsigned)((wb + 127) / 128)), dim3(128), 0, st, ws.segs.p, ws.seg_start.p, wb);
-    ZP_LAUNCH(msm_fold_kernel, dim3((unsigned)((wb + 3) / 4)), dim3(128), 0, st, ws.segs.p, ws.seg_start.p, wb);
+    ZP_CUDA(cudaMemsetAsync(ws.counter.p + 1, 0, sizeof(uint32_t), st));
+    ZP_LAUNCH(msm_fold_small_kernel, dim3((unsigned)((wb + 127) / 128)), dim3(128), 0, st, ws.segs.p, ws.seg_start.p, wb, ws.fold_list.p,
+              ws.counter.p + 1);
+    ZP_LAUNCH(msm_fold_kernel, dim3((unsigned)(ws.sm_count * 8)), dim3(128), 0, st, ws.segs.p, ws.seg_start.p, ws.fold_list.p,
+              ws.counter.p + 1);
     mark(5);
     const int groups = msm_reduce_groups(cfg), lw2 = msm_reduce_lw2(cfg);
     // threads per row / column sum: fewer threads = longer serial part but a shorter tree and more resident CTAs

@@ -68,7 +68,8 @@ struct MsmWorkspace {
     DevBuf<uint32_t> seg_cnt;  // [nwin*nbuckets]
     DevBuf<xyzz_t> segs;       // [<= nwin*n/seg + nwin*nbuckets] partial sum of each work segment
     DevBuf<uint2> desc;        // [<= nwin*n/seg + nwin*nbuckets] (first, last+1) index into `sorted` of each work segment
-    DevBuf<uint32_t> counter;  // dynamic segment counter of the persistent accumulate kernel
+    DevBuf<uint32_t> counter;  // [0] dynamic segment counter of the persistent accumulate kernel, [1] entries of fold_list
+    DevBuf<uint32_t> fold_list;// buckets split into more than 8 work segments (folded by one warp each)
     DevBuf<uint32_t> tile_sum; // scratch of the multi-CTA scan
     int sm_count = 0;
     int acc_variant = 3;       // resident CTAs per SM of the accumulate kernel (ZP_ACC_VARIANT=3|4|5)

@@ -24,14 +24,32 @@ __global__ void __launch_bounds__(256) ba_pair_count_kernel(const uint32_t* __re
 }
 
 // Slot table: src0[j] = (index of the first point of pair j) << 1 | (the slot is a real pair, not a leftover).
-// One warp per bucket run, lanes over the pairs of the run (coalesced stores; no per-slot search).
+// Eight lanes per bucket run, four runs per warp (coalesced 32-byte stores; no per-slot search): a run has ~52 / 26 / 13 / 7
+// pairs in rounds 1 - 4, and one WARP per run spent 0.3 ms per round on two million nearly empty warps.  A run with more than
+// 64 pairs (skewed scalar distributions) is written by the whole warp afterwards.
 __global__ void __launch_bounds__(256) ba_slots_kernel(const uint32_t* __restrict__ begin, const uint32_t* __restrict__ endp,
                                                        const uint32_t* __restrict__ rs, size_t nb, uint32_t* __restrict__ src0) {
-    size_t b = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t lane = threadIdx.x & 31;
-    if (b >= nb) return;
-    const uint32_t b0 = begin[b], len = endp[b] - b0, o = rs[b], np = (len + 1) >> 1;
-    for (uint32_t t = lane; t < np; t += 32) src0[o + t] = ((b0 + 2 * t) << 1) | (2 * t + 1 < len ? 1u : 0u);
+    const size_t b = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const uint32_t lane = threadIdx.x & 31, sub = lane & 7;
+    uint32_t b0 = 0, len = 0, o = 0;
+    if (b < nb) {
+        b0 = begin[b];
+        len = endp[b] - b0;
+        o = rs[b];
+    }
+    const uint32_t np = (len + 1) >> 1;
+    const bool big = np > 64;
+    if (!big)
+        for (uint32_t t = sub; t < np; t += 8) src0[o + t] = ((b0 + 2 * t) << 1) | (2 * t + 1 < len ? 1u : 0u);
+    uint32_t todo = __ballot_sync(0xffffffffu, big && sub == 0);  // every lane gets here: no early return above
+    while (todo) {
+        const int leader = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const uint32_t B0 = __shfl_sync(0xffffffffu, b0, leader), L = __shfl_sync(0xffffffffu, len, leader),
+                       O = __shfl_sync(0xffffffffu, o, leader);
+        const uint32_t NP = (L + 1) >> 1;
+        for (uint32_t t = lane; t < NP; t += 32) src0[O + t] = ((B0 + 2 * t) << 1) | (2 * t + 1 < L ? 1u : 0u);
+    }
 }
 
 // A CTA of BA_T threads covers BA_K * BA_T consecutive slots; thread tl owns slots base + k * BA_T + tl (k < BA_K), so
