@@ -280,6 +280,19 @@ __global__ void __launch_bounds__(256) msm_scatter_fused_kernel(MsmBatch batch, 
 ZP_D const affine_t* point_at(const affine_t* base, uint32_t idx, uint32_t stride) {
     return reinterpret_cast<const affine_t*>(reinterpret_cast<const unsigned char*>(base) + (size_t)idx * stride);
 }
+// Where a kernel reads its points from: an array of structures `stride` bytes apart (the SRS, a window table, a caller's
+// points) or, for the partial sums the batch-affine rounds materialise, two arrays — x[i] at base, y[i] `ysep` elements later.
+struct PointSrc {
+    const affine_t* base;
+    uint32_t stride;
+    size_t ysep;  // 0: array of structures
+};
+ZP_D fq_t point_x(const PointSrc& s, uint32_t i) {
+    return s.ysep ? load_fq(&reinterpret_cast<const fq_t*>(s.base)[i]) : load_fq(&point_at(s.base, i, s.stride)->x);
+}
+ZP_D fq_t point_y(const PointSrc& s, uint32_t i) {
+    return s.ysep ? load_fq(&reinterpret_cast<const fq_t*>(s.base)[s.ysep + i]) : load_fq(&point_at(s.base, i, s.stride)->y);
+}
 ZP_D affine_t load_affine(const affine_t* p) {
     affine_t r;
     r.x = load_fq(&p->x);
@@ -331,7 +344,7 @@ __global__ void __launch_bounds__(256) msm_segdesc_kernel(const uint32_t* __rest
 // from a global counter as soon as it finishes one, so all 32 lanes of a warp keep executing the same
 // point-addition body (no tail divergence from unequal bucket sizes).
 template <int MINBLOCKS>
-__global__ void __launch_bounds__(128, MINBLOCKS) msm_accumulate_kernel(const affine_t* __restrict__ points, uint32_t pt_stride,
+__global__ void __launch_bounds__(128, MINBLOCKS) msm_accumulate_kernel(const PointSrc ps,
                                                                         const uint32_t* __restrict__ sorted,
                                                                         const uint2* __restrict__ desc,
                                                                         const uint32_t* __restrict__ nseg_ptr,
@@ -355,7 +368,9 @@ __global__ void __launch_bounds__(128, MINBLOCKS) msm_accumulate_kernel(const af
         // (software-pipelining the gather one iteration ahead was measured slower: 32.3 vs 30.1 ms — the loop is
         // multiplier-bound, the extra 24 live registers cost more than the hidden latency)
         uint32_t e = sorted ? sorted[k] : k;  // after batch-affine rounds the run IS the point array
-        affine_t p = load_affine(point_at(points, e & 0x7fffffffu, pt_stride));
+        affine_t p;
+        p.x = point_x(ps, e & 0x7fffffffu);
+        p.y = point_y(ps, e & 0x7fffffffu);
         if (e >> 31) p.y = p.y.neg();
         acc.add_affine(p.x, p.y);
         k++;
@@ -619,8 +634,7 @@ static void msm_launch_impl(MsmWorkspace& ws, const MsmConfig& cfg, const affine
     mark(3);
     // ---- batch-affine pre-reduction rounds
     const uint32_t *run_begin = ws.start.p, *run_end = ws.cursor.p, *entries = ws.sorted.p;
-    const affine_t* pts = points;
-    uint32_t pstride = cfg.pt_stride;  // the materialised partial sums of the batch-affine rounds are packed affine_t
+    PointSrc ps{points, cfg.pt_stride, 0};  // the batch-affine rounds materialise their partial sums as x[] / y[] arrays
     size_t est = wn;  // upper bound on the bucket entries still to be added
     const bool bucket_slice = cfg.bucket_lg > 0;
     if (bucket_slice) {
@@ -653,34 +667,17 @@ static void msm_launch_impl(MsmWorkspace& ws, const MsmConfig& cfg, const affine
         for (int r = 0; r < rounds; r++) {
             size_t cap = est / 2 + wb;
             uint32_t* rs = ws.ba_rs[r & 1].p;
-            affine_t* out = ws.ba_pts[r & 1].p;
+            // this round's partial sums: x[0 .. cap) then y[0 .. cap) in the ping-pong buffer (cap * 96 bytes)
+            fq_t* out_x = reinterpret_cast<fq_t*>(ws.ba_pts[r & 1].p);
+            fq_t* out_y = out_x + cap;
             unsigned nblk = (unsigned)((cap + BA_K * BA_T - 1) / (BA_K * BA_T));
             size_t m = (size_t)nblk * BA_T;
             ZP_LAUNCH(ba_pair_count_kernel, dim3((unsigned)((wb + 255) / 256)), dim3(256), 0, st, run_begin, run_end, wb, ws.ba_cnt.p);
             msm_scan(ws.ba_cnt.p, rs, wb, ws.tile_sum.p, st);
             ZP_LAUNCH(ba_slots_kernel, dim3((unsigned)((wb * 8 + 255) / 256)), dim3(256), 0, st, run_begin, run_end, rs, wb,
                       ws.ba_src.p);
-            static const int ba_pf = getenv("ZP_BA_PF") ? atoi(getenv("ZP_BA_PF")) : 0;
-            static const int ba_ng = getenv("ZP_BA_NG") ? atoi(getenv("ZP_BA_NG")) : 1;
-            if (ba_ng == 2) {
-                auto k = ba_up0_ng_kernel<2>;
-                ZP_LAUNCH(k, dim3((nblk + 1) / 2), dim3(BA_T), 0, st, ws.ba_src.p, rs + wb, cap, entries, pts, pstride, ws.ba_pre.p, ws.ba_den.p, ws.ba_flag.p, nblk);
-            } else if (ba_ng == 4) {
-                auto k = ba_up0_ng_kernel<4>;
-                ZP_LAUNCH(k, dim3((nblk + 3) / 4), dim3(BA_T), 0, st, ws.ba_src.p, rs + wb, cap, entries, pts, pstride, ws.ba_pre.p, ws.ba_den.p, ws.ba_flag.p, nblk);
-            } else if (ba_pf == 1) {
-                auto k = ba_up0_pf_kernel<1>;
-                ZP_LAUNCH(k, dim3(nblk), dim3(BA_T), 0, st, ws.ba_src.p, rs + wb, cap, entries, pts, pstride, ws.ba_pre.p, ws.ba_den.p, ws.ba_flag.p);
-            } else if (ba_pf == 2) {
-                auto k = ba_up0_pf_kernel<2>;
-                ZP_LAUNCH(k, dim3(nblk), dim3(BA_T), 0, st, ws.ba_src.p, rs + wb, cap, entries, pts, pstride, ws.ba_pre.p, ws.ba_den.p, ws.ba_flag.p);
-            } else if (ba_pf == 4) {
-                auto k = ba_up0_pf_kernel<4>;
-                ZP_LAUNCH(k, dim3(nblk), dim3(BA_T), 0, st, ws.ba_src.p, rs + wb, cap, entries, pts, pstride, ws.ba_pre.p, ws.ba_den.p, ws.ba_flag.p);
-            } else {
-                ZP_LAUNCH(ba_up0_kernel, dim3(nblk), dim3(BA_T), 0, st, ws.ba_src.p, rs + wb, cap, entries, pts, pstride, ws.ba_pre.p,
-                          ws.ba_den.p, ws.ba_flag.p);
-            }
+            ZP_LAUNCH(ba_up0_kernel, dim3(nblk), dim3(BA_T), 0, st, ws.ba_src.p, rs + wb, cap, entries, ps, ws.ba_pre.p, ws.ba_den.p,
+                      ws.ba_flag.p);
             fq_batch_inverse(ws.ba_den.p, m, ws.ba_den.p + m, ws.ba_root.get(), st);
             if (stats) {
                 if (!ws.down_ev[2 * r]) {
@@ -689,14 +686,13 @@ static void msm_launch_impl(MsmWorkspace& ws, const MsmConfig& cfg, const affine
                 }
                 ZP_CUDA(cudaEventRecord(ws.down_ev[2 * r], st));
             }
-            ZP_LAUNCH(ba_down0_kernel, dim3(nblk), dim3(BA_T), 0, st, ws.ba_src.p, rs + wb, cap, entries, pts, pstride, ws.ba_pre.p,
-                      ws.ba_den.p, out);
+            ZP_LAUNCH(ba_down0_kernel, dim3(nblk), dim3(BA_T), 0, st, ws.ba_src.p, rs + wb, cap, entries, ps, ws.ba_pre.p,
+                      ws.ba_den.p, out_x, out_y);
             if (stats) ZP_CUDA(cudaEventRecord(ws.down_ev[2 * r + 1], st));
             run_begin = rs;
             run_end = rs + 1;
             entries = nullptr;
-            pts = out;
-            pstride = (uint32_t)sizeof(affine_t);
+            ps = PointSrc{reinterpret_cast<const affine_t*>(out_x), 0u, cap};
             est = cap;
         }
     }
@@ -728,13 +724,13 @@ static void msm_launch_impl(MsmWorkspace& ws, const MsmConfig& cfg, const affine
         unsigned grid = (unsigned)(ws.sm_count * blocks_per_sm);
         if (variant == 4) {
             auto k = msm_accumulate_kernel<4>;
-            ZP_LAUNCH(k, dim3(grid), dim3(128), 0, st, pts, pstride, entries, ws.desc.p, ws.seg_start.p + wb, ws.counter.p, ws.segs.p);
+            ZP_LAUNCH(k, dim3(grid), dim3(128), 0, st, ps, entries, ws.desc.p, ws.seg_start.p + wb, ws.counter.p, ws.segs.p);
         } else if (variant == 5) {
             auto k = msm_accumulate_kernel<5>;
-            ZP_LAUNCH(k, dim3(grid), dim3(128), 0, st, pts, pstride, entries, ws.desc.p, ws.seg_start.p + wb, ws.counter.p, ws.segs.p);
+            ZP_LAUNCH(k, dim3(grid), dim3(128), 0, st, ps, entries, ws.desc.p, ws.seg_start.p + wb, ws.counter.p, ws.segs.p);
         } else {
             auto k = msm_accumulate_kernel<3>;
-            ZP_LAUNCH(k, dim3(grid), dim3(128), 0, st, pts, pstride, entries, ws.desc.p, ws.seg_start.p + wb, ws.counter.p, ws.segs.p);
+            ZP_LAUNCH(k, dim3(grid), dim3(128), 0, st, ps, entries, ws.desc.p, ws.seg_start.p + wb, ws.counter.p, ws.segs.p);
         }
     }
     ZP_CUDA(cudaMemsetAsync(ws.counter.p + 1, 0, sizeof(uint32_t), st));

@@ -5,8 +5,9 @@
 // with all inversions of a round shared through one parallel Montgomery batch inversion (3 products per element: the
 // leaf level is fused with the denominators on the way up and with the additions on the way down), i.e. ~6 Fq products
 // per addition instead of the 10 of an XYZZ mixed addition.  Each round halves the run lengths and
-// materialises the partial sums contiguously, so later rounds and the final accumulation read sequential memory instead
-// of gathering from the SRS table.  A pair with x1 == x2 (P + P or P - P; impossible for distinct SRS powers, reachable
+// materialises the partial sums contiguously — all x-coordinates, then all y-coordinates (SoA), so that the next round's
+// upward pass streams the x array only — and later rounds and the final accumulation read sequential memory instead of
+// gathering from the SRS table.  A pair with x1 == x2 (P + P or P - P; impossible for distinct SRS powers, reachable
 // with repeated input points) raises a flag and the whole MSM is redone on the plain XYZZ path, so the result is exact
 // for every input.
 #pragma once
@@ -61,8 +62,7 @@ static const int BA_T = 256;
 // slot): pre[j] = product of the group's denominators before slot j (k >= 1), up[group] = product of all BA_K.
 // The denominators themselves are not stored: the downward kernel reloads both points anyway.
 __global__ void __launch_bounds__(BA_T) ba_up0_kernel(const uint32_t* __restrict__ src0, const uint32_t* __restrict__ total_ptr,
-                                                      size_t cap, const uint32_t* __restrict__ entries,
-                                                      const affine_t* __restrict__ pts, uint32_t pstride,
+                                                      size_t cap, const uint32_t* __restrict__ entries, const PointSrc ps,
                                                       fq_t* __restrict__ pre, fq_t* __restrict__ up,
                                                       uint32_t* __restrict__ flag) {
     const size_t base = (size_t)blockIdx.x * (BA_K * BA_T) + threadIdx.x;
@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(BA_T) ba_up0_kernel(const uint32_t* __restrict
             if (s & 1u) {
                 const uint32_t i0 = s >> 1;
                 const uint32_t e0 = entries ? entries[i0] & 0x7fffffffu : i0, e1 = entries ? entries[i0 + 1] & 0x7fffffffu : i0 + 1;
-                d = load_fq(&point_at(pts, e1, pstride)->x) - load_fq(&point_at(pts, e0, pstride)->x);
+                d = point_x(ps, e1) - point_x(ps, e0);
                 pair = true;
                 if (d.is_zero()) {
                     *flag = 1;
@@ -96,150 +96,16 @@ __global__ void __launch_bounds__(BA_T) ba_up0_kernel(const uint32_t* __restrict
 }
 
 
-// EXPERIMENT (ZP_BA_NG = 2 | 4): NG leaf groups per thread walked in lock step, i.e. NG independent gather -> product chains
-// in flight per thread instead of one (same outputs, same layout as ba_up0_kernel).
-template <int NG>
-__global__ void __launch_bounds__(BA_T) ba_up0_ng_kernel(const uint32_t* __restrict__ src0, const uint32_t* __restrict__ total_ptr,
-                                                         size_t cap, const uint32_t* __restrict__ entries,
-                                                         const affine_t* __restrict__ pts, uint32_t pstride,
-                                                         fq_t* __restrict__ pre, fq_t* __restrict__ up, uint32_t* __restrict__ flag,
-                                                         unsigned ngroups) {
-    const size_t total = *total_ptr;
-    fq_t acc[NG];
-    size_t base[NG];
-    bool live[NG];
-#pragma unroll
-    for (int g = 0; g < NG; g++) {
-        const unsigned grp = blockIdx.x * NG + g;
-        live[g] = grp < ngroups;
-        base[g] = (size_t)grp * (BA_K * BA_T) + threadIdx.x;
-        acc[g] = fq_t::one();
-    }
-#pragma unroll 1
-    for (int k = 0; k < BA_K; k++) {
-        fq_t d[NG];
-        bool pair[NG];
-#pragma unroll
-        for (int g = 0; g < NG; g++) {
-            const size_t j = base[g] + (size_t)k * BA_T;
-            pair[g] = false;
-            if (live[g] && j < cap && j < total) {
-                const uint32_t s = src0[j];
-                if (s & 1u) {
-                    const uint32_t i0 = s >> 1;
-                    const uint32_t e0 = entries ? entries[i0] & 0x7fffffffu : i0, e1 = entries ? entries[i0 + 1] & 0x7fffffffu : i0 + 1;
-                    d[g] = load_fq(&point_at(pts, e1, pstride)->x) - load_fq(&point_at(pts, e0, pstride)->x);
-                    pair[g] = true;
-                }
-            }
-        }
-#pragma unroll
-        for (int g = 0; g < NG; g++) {
-            const size_t j = base[g] + (size_t)k * BA_T;
-            if (!live[g] || j >= cap) continue;
-            if (pair[g] && d[g].is_zero()) {
-                *flag = 1;
-                pair[g] = false;
-            }
-            if (!pair[g]) d[g] = fq_t::one();
-            if (k) store_fq(&pre[j], acc[g]);
-            if (k == 0) acc[g] = d[g];
-            else if (pair[g]) acc[g] = acc[g] * d[g];
-        }
-    }
-#pragma unroll
-    for (int g = 0; g < NG; g++)
-        if (live[g]) store_fq(&up[(size_t)(blockIdx.x * NG + g) * BA_T + threadIdx.x], acc[g]);
-}
-
-ZP_D void prefetch_l2(const void* p) {
-#ifndef ZP_EMU
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-#else
-    (void)p;
-#endif
-}
-
-// EXPERIMENT (ZP_BA_PF = 1 | 2 | 4, default off): the x-coordinate gathers are random 128-byte lines out of a multi-GiB
-// table; with one dependent gather per loop iteration the kernel above runs at 45 % of DRAM bandwidth (ncu, round 1).
-// This variant walks a thread's slots in chunks of BA_PF: the indices of the NEXT chunk are resolved and their lines
-// requested with prefetch.global.L2 (no registers held) while the current chunk's lines are consumed.  Measured SLOWER at
-// every distance (profiles/r02i_msm_up0_prefetch.log): the prefetched footprint of all resident threads approaches the L2.
-template <int BA_PF>
-__global__ void __launch_bounds__(BA_T) ba_up0_pf_kernel(const uint32_t* __restrict__ src0, const uint32_t* __restrict__ total_ptr,
-                                                      size_t cap, const uint32_t* __restrict__ entries,
-                                                      const affine_t* __restrict__ pts, uint32_t pstride,
-                                                      fq_t* __restrict__ pre, fq_t* __restrict__ up,
-                                                      uint32_t* __restrict__ flag) {
-    const size_t base = (size_t)blockIdx.x * (BA_K * BA_T) + threadIdx.x;
-    const size_t total = *total_ptr;
-    fq_t acc = fq_t::one();
-    uint32_t ea[BA_PF], eb[BA_PF], na[BA_PF], nb[BA_PF];
-    uint32_t pair_cur = 0, pair_next = 0;  // bit i: slot i of the chunk is a real pair
-    auto resolve = [&](int chunk, uint32_t* a, uint32_t* b) -> uint32_t {
-        uint32_t mask = 0;
-#pragma unroll
-        for (int i = 0; i < BA_PF; i++) {
-            const size_t j = base + (size_t)(chunk * BA_PF + i) * BA_T;
-            a[i] = b[i] = 0;
-            if (j < cap && j < total) {
-                const uint32_t s = src0[j];
-                if (s & 1u) {
-                    const uint32_t i0 = s >> 1;
-                    a[i] = entries ? entries[i0] & 0x7fffffffu : i0;
-                    b[i] = entries ? entries[i0 + 1] & 0x7fffffffu : i0 + 1;
-                    mask |= 1u << i;
-                }
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < BA_PF; i++)
-            if ((mask >> i) & 1u) {
-                prefetch_l2(&point_at(pts, a[i], pstride)->x);
-                prefetch_l2(&point_at(pts, b[i], pstride)->x);
-            }
-        return mask;
-    };
-    pair_cur = resolve(0, ea, eb);
-#pragma unroll 1
-    for (int chunk = 0; chunk < BA_K / BA_PF; chunk++) {
-        if (chunk + 1 < BA_K / BA_PF) pair_next = resolve(chunk + 1, na, nb);
-#pragma unroll
-        for (int i = 0; i < BA_PF; i++) {
-            const int k = chunk * BA_PF + i;
-            const size_t j = base + (size_t)k * BA_T;
-            if (j >= cap) break;
-            bool pair = (pair_cur >> i) & 1u;
-            fq_t d;
-            if (pair) {
-                d = load_fq(&point_at(pts, eb[i], pstride)->x) - load_fq(&point_at(pts, ea[i], pstride)->x);
-                if (d.is_zero()) {
-                    *flag = 1;
-                    pair = false;
-                }
-            }
-            if (!pair) d = fq_t::one();
-            if (k) store_fq(&pre[j], acc);
-            if (k == 0) acc = d;
-            else if (pair) acc = acc * d;
-        }
-#pragma unroll
-        for (int i = 0; i < BA_PF; i++) {
-            ea[i] = na[i];
-            eb[i] = nb[i];
-        }
-        pair_cur = pair_next;
-    }
-    store_fq(&up[(size_t)blockIdx.x * BA_T + threadIdx.x], acc);
-}
+// (Two variants of this kernel — software prefetch of the next slots' lines with prefetch.global.L2, and 2 / 4 leaf groups
+// per thread in lock step — were measured slower, profiles/r02j_msm_up0_variants.log, and removed: the kernel runs at the
+// random-line rate of the memory system in round 1.)
 
 // Leaf level downwards fused with the additions: from inv = 1 / (product of the group) recover each 1 / den[j]
 // (2 products per slot with the stored prefix products) and emit out[j] = P(i0) + P(i0 + 1), or the leftover point.
 __global__ void __launch_bounds__(BA_T, 2) ba_down0_kernel(const uint32_t* __restrict__ src0, const uint32_t* __restrict__ total_ptr,
-                                                        size_t cap, const uint32_t* __restrict__ entries,
-                                                        const affine_t* __restrict__ pts, uint32_t pstride,
+                                                        size_t cap, const uint32_t* __restrict__ entries, const PointSrc ps,
                                                         const fq_t* __restrict__ pre, const fq_t* __restrict__ up_inv,
-                                                        affine_t* __restrict__ out) {
+                                                        fq_t* __restrict__ out_x, fq_t* __restrict__ out_y) {
     const size_t base = (size_t)blockIdx.x * (BA_K * BA_T) + threadIdx.x;
     const size_t total = *total_ptr;
     if (base >= total) return;  // slots of one thread ascend with k: nothing to emit
@@ -251,13 +117,11 @@ __global__ void __launch_bounds__(BA_T, 2) ba_down0_kernel(const uint32_t* __res
         const uint32_t s = src0[j];
         const uint32_t i0 = s >> 1;
         const uint32_t e0 = entries ? entries[i0] : i0;
-        const affine_t* p0 = point_at(pts, e0 & 0x7fffffffu, pstride);
-        fq_t x1 = load_fq(&p0->x), y1 = load_fq(&p0->y);
+        fq_t x1 = point_x(ps, e0 & 0x7fffffffu), y1 = point_y(ps, e0 & 0x7fffffffu);
         if (entries && (e0 >> 31)) y1 = y1.neg();
         if (s & 1u) {
             const uint32_t e1 = entries ? entries[i0 + 1] : i0 + 1;
-            const affine_t* p1 = point_at(pts, e1 & 0x7fffffffu, pstride);
-            fq_t x2 = load_fq(&p1->x), y2 = load_fq(&p1->y);
+            fq_t x2 = point_x(ps, e1 & 0x7fffffffu), y2 = point_y(ps, e1 & 0x7fffffffu);
             if (entries && (e1 >> 31)) y2 = y2.neg();
             fq_t d = x2 - x1;
             if (!d.is_zero()) {  // a degenerate pair was given den = 1 (the whole MSM is redone anyway)
@@ -272,8 +136,8 @@ __global__ void __launch_bounds__(BA_T, 2) ba_down0_kernel(const uint32_t* __res
                 x1 = x3;
             }
         }
-        store_fq(&out[j].x, x1);
-        store_fq(&out[j].y, y1);
+        store_fq(&out_x[j], x1);
+        store_fq(&out_y[j], y1);
     }
 }
 
