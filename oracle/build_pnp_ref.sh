@@ -5,7 +5,9 @@
 # "Prize 1B/plonk-core/build.rs":36-103 (blst: gcc -O2 -mno-avx; everything else: nvcc -std=c++17 -O3, here
 # -arch=sm_100 instead of sm_80).  The result exports the reference's `gen_proof` symbol and is used ONLY by
 # tests/test_gpu_vs_pnp_reference.py to cross-run the reference on the GPU box against the oracle and against
-# our library (SURVEY §8c pin (5); valid for Merkle-shaped inputs).
+# our library (SURVEY §8c pin (5); valid for Merkle-shaped inputs).  A second library,
+# oracle/_ref/libzprize_ref_patched.so, is the same build with three translation units patched at build time (below): the
+# unmodified one dies above HEIGHT=4 from its own double destruction of shared buffers; the patched one proves HEIGHT=15.
 set -euo pipefail
 cd "$(dirname "$0")"
 REF="${ZP_REFERENCE_ROOT:-/root/reference}/Prize 1B/plonk-core/lib"
@@ -23,6 +25,7 @@ build_ops() {
 }
 PATCHED=_ref/libzprize_ref_patched.so
 [ -f "$OUT" ] && [ -f "$PATCHED" ] && { echo "$OUT exists"; build_ops; exit 0; }
+rm -rf _ref/pnp_obj && mkdir -p _ref/pnp_obj   # leftovers of an interrupted build
 gcc -O2 -mno-avx -fno-builtin -Wno-unused-function -fPIC -D__BLST_PORTABLE__ -I"$REF/blst/include" \
     -c "$REF/blst/src/server.c" -o _ref/pnp_obj/blst_server.o
 gcc -O2 -fPIC -c "$REF/blst/src/assembly.S" -o _ref/pnp_obj/blst_asm.o

@@ -22,12 +22,13 @@ def main():
     ap.add_argument("--out", required=True)
     ap.add_argument("--repeat", type=int, default=1)
     ap.add_argument("--lib", default="libzprize_ref.so",
-                    help="libzprize_ref.so (unmodified) or libzprize_ref_patched.so (split_tx_poly bounds patch, see oracle/build_pnp_ref.sh)")
+                    help="libzprize_ref.so (unmodified; dies above HEIGHT=4 on this box) or libzprize_ref_patched.so (the reference's double "
+                         "destruction and 18-byte MSM result buffer fixed at build time, see oracle/build_pnp_ref.sh)")
     args = ap.parse_args()
     pkg = load_package()
     trace = os.path.join(ROOT, "oracle", "libsegv_trace.so")
     if os.path.exists(trace) and not os.environ.get("ZP_NO_SEGV_TRACE"):
-        ctypes.CDLL(trace)  # native backtrace on SIGSEGV: the reference's own code crashes above HEIGHT=4 on some runs
+        ctypes.CDLL(trace)  # native backtrace on SIGSEGV: the UNMODIFIED reference crashes above HEIGHT=4
     path = os.path.join(ROOT, "oracle", "_ref", args.lib)
     ref = ctypes.CDLL(path)
     ref.gen_proof.restype = pkg.ProofC
