@@ -15,6 +15,7 @@ ranks, rank 0 prints ONE JSON line.  A "step" is one full gen_proof of the same 
 import argparse
 import json
 import os
+import re
 import subprocess
 import sys
 import threading
@@ -147,6 +148,45 @@ def cpu_baseline_sample(height, steps, warmup):
     return float(np.mean(times)), n_sample, int(orc.lib.zpo_num_threads())
 
 
+def parse_reference_gpu_log(text):
+    """(per-call seconds, proof == pinned oracle proof or None) out of tools/run_pnp_reference.py's output."""
+    calls = [float(x) for x in re.findall(r"reference gen_proof call \d+: ([0-9.]+) s", text)]
+    same = re.search(r"equals the oracle's proof: (True|False)", text)
+    return calls, (same.group(1) == "True") if same else None
+
+
+def reference_native_gpu(height, repeat=3, timeout_s=420):
+    """Same-box GPU figure beside the CPU arm: the reference's OWN native prover (PNP lib/, compiled for sm_100 where it lies
+    by oracle/build_pnp_ref.sh; the library with its double destruction patched — unmodified it cannot run above HEIGHT=4 on
+    this box) proving the same circuit through its gen_proof FFI symbol with host key arrays.  Runs in a
+    subprocess (the reference exits the process on errors); informational — the arm's `value` stays the CPU prover."""
+    lib = os.path.join(ROOT, "oracle", "_ref", "libzprize_ref_patched.so")
+    if not os.path.exists(lib):
+        return {"unavailable": "oracle/_ref/libzprize_ref_patched.so not built (oracle/build_pnp_ref.sh needs /root/reference)"}
+    try:
+        gpus = subprocess.run(["nvidia-smi", "-L"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=20)
+        if gpus.returncode != 0 or "GPU 0" not in gpus.stdout:
+            return {"unavailable": "no CUDA device"}
+    except Exception:  # noqa: BLE001
+        return {"unavailable": "no CUDA device"}
+    out = "/tmp/zp_bench_reference_gpu_proof.npy"
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "run_pnp_reference.py"), "--height", str(height),
+                            "--repeat", str(repeat), "--lib", "libzprize_ref_patched.so", "--out", out],
+                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout_s,
+                           env=dict(os.environ, OMP_NUM_THREADS=str(host_threads())))
+    except subprocess.TimeoutExpired:
+        return {"unavailable": "reference native prover did not finish in %d s" % timeout_s}
+    calls, same = parse_reference_gpu_log(r.stdout)
+    if r.returncode != 0 or not calls:
+        return {"unavailable": "reference native prover exited with code %d" % r.returncode}
+    return {"unit": "s", "calls_s": calls, "best_s": min(calls), "median_s": float(np.median(calls)),
+            "proof_equals_pinned_oracle_proof": same,
+            "what": "the reference's own native prover (oracle/_ref/libzprize_ref_patched.so: PNP lib/ for sm_100, its double "
+                    "destruction in quotient.cu and 18-byte MSM result buffer patched at build time) on this box's GPU 0, "
+                    "gen_proof(CircuitC, ProverKeyC, CommitKeyC) with host key arrays, HEIGHT=%d" % height}
+
+
 def run_reference(args, rank):
     """Reference arm: the CPU prover on the box's host cores AT THE HEADLINE CONFIG (one step = one full HEIGHT=15
     gen_proof, ~1-2 min of CPU each).  Bounded: at least one proof, more only while the run stays inside --ref-budget
@@ -185,6 +225,8 @@ def run_reference(args, rank):
         "cpu_baseline": {"value": est, "unit": "s", "cores": info["threads"], "kind": "port", "sample": sample},
         "e2e": {"value": est, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    if args.gpus == 1 and not args.no_reference_gpu:
+        line["reference_gpu_same_box"] = reference_native_gpu(args.height)  # the CPU circuit above is already freed
     print(json.dumps(line), flush=True)
 
 
@@ -245,6 +287,8 @@ def main():
     ap.add_argument("--no-drop-in", action="store_true", dest="no_drop_in",
                     help="skip the cold / cloned-key measurement of the literal gen_proof symbol")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reference-gpu", action="store_true", dest="no_reference_gpu",
+                    help="reference arm at 1 GPU: do not also run the reference's own native GPU prover (informational key)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
