@@ -1,13 +1,14 @@
 // Pippenger MSM over BLS12-381 G1 for sm_100a — see msm.cuh / DESIGN.md §MSM.
 //
-// Pipeline of one batch of k <= 8 scalar vectors over the same points (all on one stream; host round trips: the root
-// inversion of each batch-affine round and the k final sums):
+// Pipeline of one batch of k <= 8 scalar vectors over the same points (all on one stream; host round trips: the top of the
+// inversion tree of each batch-affine round and the k final sums):
 //   1. digits    : Montgomery scalar -> canonical -> signed c-bit digits, per-(member, window / set, bucket) histogram
 //   2. scan      : exclusive scan of the histogram (bucket start offsets), multi-CTA
 //   3. scatter   : counting-sort the point indices into bucket runs (atomic cursor per bucket)
-//   4. rounds    : batch-affine pairwise additions inside every run (msm_affine.cuh), 4 rounds by default
+//   4. rounds    : batch-affine pairwise additions inside every run (msm_affine.cuh), 4 rounds by default; every round
+//                  writes its partial sums as x[] / y[] arrays that the next round reads sequentially
 //   5. accumulate: what is left (1/16 of the entries): one thread per work segment, XYZZ mixed additions, persistent
-//                  threads; long buckets are split so no digit distribution serialises
+//                  threads; long buckets are split so no digit distribution serialises (and folded back from a work list)
 //   6. reduce    : row / column sums of the bucket matrix, then weight * sum and a tree (msm_rowcol_kernel, msm_weighted_kernel)
 //   host         : with precomputed window tables one XYZZ point per member; otherwise Horner over the window sums; to affine
 // Multi-GPU (precomputed tables only): ranks split the BUCKETS, not the points.  A launch with cfg.bucket_lg = log2 G keeps
