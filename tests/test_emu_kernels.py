@@ -86,6 +86,24 @@ def test_gen_proof_byte_identical_under_emulation(pkg, emu_lib, oracle, n_lookup
     oc.close()
 
 
+@pytest.mark.parametrize("n_lookup", [0, 12])
+def test_gen_proof_with_second_stream_ntts_under_emulation(pkg, emu_lib, oracle, monkeypatch, n_lookup):
+    """ZP_NTT_OVERLAP=1 (experiment, off by default): wire and z(X) coset NTTs forked onto the second stream and joined before
+    the quotient pass — the fork / join bookkeeping and the skipped jobs give the same proof bytes (the emulation runs the
+    streams in program order; the race-freedom of the real streams is what the GPU parity test checks)."""
+    monkeypatch.setenv("ZP_NTT_OVERLAP", "1")  # read when the context is created
+    oc = oracle_lib.OracleCircuit(oracle, 3, 42, 7, n_lookup)
+    ref_proof, _ = oc.prove()
+    c = pkg.ProverContext(oc.log_n, emu_lib)
+    c.load_srs(oc.srs())
+    c.preprocess(oc.selector_evals(), oc.tables())
+    circ = pkg.make_circuit(oc.cs_n, oc.lookup_len, oc.pi_pos, oc.q_lookup(), oc.pi_canonical(), *oc.wires())
+    assert np.array_equal(c.prove(circ).to_words(), ref_proof)
+    assert np.array_equal(c.prove(circ).to_words(), ref_proof)
+    c.close()
+    oc.close()
+
+
 def test_gen_proof_with_precomputed_msm_tables(pkg, emu_lib, oracle, monkeypatch):
     """Same proof bytes when the commitments go through the precomputed-window MSM tables (forced on for tiny N)."""
     monkeypatch.setenv("ZP_MSM_PRECOMP_MIN_LOG", "8")
